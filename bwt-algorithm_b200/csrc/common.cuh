@@ -1,0 +1,93 @@
+// common.cuh -- shared helpers for libbwtk (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bwtk.h"
+
+namespace bwtk {
+
+void set_error(const char *fmt, ...);
+void count_launch(int k = 1);
+
+#define BWTK_CUDA(expr)                                                              \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            bwtk::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,            \
+                            cudaGetErrorString(_e));                                 \
+            return BWTK_ECUDA;                                                       \
+        }                                                                            \
+    } while (0)
+
+#define BWTK_LAUNCH_CHECK()                                                          \
+    do {                                                                             \
+        bwtk::count_launch();                                                        \
+        cudaError_t _e = cudaGetLastError();                                         \
+        if (_e != cudaSuccess) {                                                     \
+            bwtk::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,        \
+                            cudaGetErrorString(_e));                                 \
+            return BWTK_ECUDA;                                                       \
+        }                                                                            \
+    } while (0)
+
+#define BWTK_REQUIRE(cond, msg)                                                      \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            bwtk::set_error("%s:%d: %s", __FILE__, __LINE__, msg);                   \
+            return BWTK_EINVAL;                                                      \
+        }                                                                            \
+    } while (0)
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Carves aligned sub-buffers out of a caller-provided workspace.
+struct Carver {
+    char *base;
+    int64_t off, cap;
+    Carver(void *p, int64_t bytes) : base((char *)p), off(0), cap(bytes) {}
+    template <typename T> T *take(int64_t count)
+    {
+        off = align_up(off, 256);
+        T *r = (T *)(base + off);
+        off += count * (int64_t)sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+static const int NUM_SMS = 148;  // B200
+
+// ---- bit-packed text ---------------------------------------------------------
+// Symbols are stored with `bits` bits each, MSB first, in a stream of 32-bit
+// words: symbol i occupies stream bits [i*bits, (i+1)*bits).  Positions past the
+// end read as zero.  The stream is padded with 3 zero words.
+__device__ __forceinline__ uint32_t window32(const uint32_t *__restrict__ p, int64_t bitoff)
+{
+    int64_t w = bitoff >> 5;
+    uint32_t r = (uint32_t)bitoff & 31u;
+    uint32_t a = __ldg(p + w), b = __ldg(p + w + 1);
+    return __funnelshift_l(b, a, r);
+}
+
+__device__ __forceinline__ uint64_t window64(const uint32_t *__restrict__ p, int64_t bitoff)
+{
+    int64_t w = bitoff >> 5;
+    uint32_t r = (uint32_t)bitoff & 31u;
+    uint32_t a = __ldg(p + w), b = __ldg(p + w + 1), c = __ldg(p + w + 2);
+    uint32_t hi = __funnelshift_l(b, a, r), lo = __funnelshift_l(c, b, r);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+}  // namespace bwtk

@@ -1,0 +1,361 @@
+// index.cu -- byte histogram (C array), bit-packing, BWT + Occ checkpoints, LCP.
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <atomic>
+
+namespace bwtk {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int k) { g_launches += k; }
+
+// ------------------------------------------------------------------ histogram
+__global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restrict__ text, int64_t n,
+                                                        unsigned long long *__restrict__ out)
+{
+    __shared__ unsigned int s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    // aligned 16-byte body, byte-wise head and tail
+    uintptr_t addr = (uintptr_t)text;
+    int64_t head = (int64_t)((16 - (addr & 15)) & 15);
+    if (head > n) head = n;
+    int64_t body = (n - head) / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(text + head);
+    int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t last = 256, run = 0;
+    auto add = [&](uint32_t b) {
+        if (b == last) {
+            run++;
+        } else {
+            if (run) atomicAdd(&s_h[last], run);
+            last = b;
+            run = 1;
+        }
+    };
+    for (int64_t i = gtid; i < body; i += gstride) {
+        uint4 q = __ldg(v + i);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            add(w[j] & 255u); add((w[j] >> 8) & 255u); add((w[j] >> 16) & 255u); add(w[j] >> 24);
+        }
+    }
+    if (gtid < head) add(text[gtid]);
+    int64_t tail0 = head + body * 16;
+    if (tail0 + gtid < n && gtid < 16) add(text[tail0 + gtid]);
+    if (run) atomicAdd(&s_h[last], run);
+    __syncthreads();
+    unsigned int c = s_h[threadIdx.x];
+    if (c) atomicAdd(&out[threadIdx.x], (unsigned long long)c);
+}
+
+int byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, unsigned long long *d_scratch,
+                   cudaStream_t st)
+{
+    BWTK_CUDA(cudaMemsetAsync(d_scratch, 0, 256 * sizeof(unsigned long long), st));
+    if (n > 0) {
+        int64_t want = ceil_div(n, 256 * 64);
+        int grid = (int)(want < 1 ? 1 : (want > NUM_SMS * 8 ? NUM_SMS * 8 : want));
+        byte_hist_kernel<<<grid, 256, 0, st>>>(d_text, n, d_scratch);
+        BWTK_LAUNCH_CHECK();
+    }
+    BWTK_CUDA(cudaMemcpyAsync(h_totals, d_scratch, 256 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    return BWTK_OK;
+}
+
+// ------------------------------------------------------------------ packing
+int64_t packed_words(int64_t n, int bits) { return ceil_div(n * bits, 32) + 4; }
+
+// one thread per output word; bits in {1,2,4,8}
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ text, int64_t n,
+                                                   const uint8_t *__restrict__ lut, int bits,
+                                                   uint32_t *__restrict__ packed, int64_t nwords)
+{
+    __shared__ uint8_t s_lut[256];
+    __shared__ uint8_t s_in[256 * 32];
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    const int spw = 32 / bits;  // symbols per word
+    const int64_t w0 = (int64_t)blockIdx.x * 256;
+    const int64_t b0 = w0 * spw;
+    const int tile_bytes = 256 * spw;
+    for (int i = threadIdx.x; i < tile_bytes; i += 256) {
+        int64_t g = b0 + i;
+        s_in[i] = g < n ? __ldg(text + g) : 0;
+    }
+    __syncthreads();
+    int64_t w = w0 + threadIdx.x;
+    if (w >= nwords) return;
+    uint32_t acc = 0;
+    const uint8_t *src = s_in + threadIdx.x * spw;
+    int64_t sym0 = w * spw;
+    for (int j = 0; j < spw; j++) {
+        uint32_t code = (sym0 + j < n) ? s_lut[src[j]] : 0u;
+        acc = (acc << bits) | code;
+    }
+    packed[w] = acc;
+}
+
+int pack_text(const uint8_t *d_text, int64_t n, const uint8_t *h_lut, int bits, uint32_t *d_packed,
+              uint8_t *d_lut_scratch, cudaStream_t st)
+{
+    BWTK_CUDA(cudaMemcpyAsync(d_lut_scratch, h_lut, 256, cudaMemcpyHostToDevice, st));
+    int64_t nwords = packed_words(n, bits);
+    pack_kernel<<<(unsigned)ceil_div(nwords, 256), 256, 0, st>>>(d_text, n, d_lut_scratch, bits,
+                                                                 d_packed, nwords);
+    BWTK_LAUNCH_CHECK();
+    // the LUT came from the caller's stack: make sure the copy has been consumed
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    return BWTK_OK;
+}
+
+// Chooses the packing of a text: returns bits, fills lut; *fast = ACGT$ layout
+// ('$' shares code 0 with 'A').
+int choose_packing(const uint8_t *d_text, int64_t n, const int64_t *totals, uint8_t *lut, bool *fast,
+                   cudaStream_t st)
+{
+    memset(lut, 0, 256);
+    int sigma = 0;
+    for (int b = 0; b < 256; b++) sigma += totals[b] > 0;
+    int64_t acgt = totals['A'] + totals['C'] + totals['G'] + totals['T'];
+    *fast = (n > 0 && totals['$'] == 1 && acgt == n - 1);
+    if (*fast) {
+        uint8_t last = 0;
+        if (cudaMemcpyAsync(&last, d_text + n - 1, 1, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            return -1;
+        *fast = (last == '$');
+    }
+    if (*fast) {
+        lut['A'] = 0; lut['C'] = 1; lut['G'] = 2; lut['T'] = 3; lut['$'] = 0;
+        return 2;
+    }
+    int d = 0;
+    for (int b = 0; b < 256; b++)
+        if (totals[b] > 0) lut[b] = (uint8_t)d++;
+    return sigma <= 2 ? 1 : sigma <= 4 ? 2 : sigma <= 16 ? 4 : 8;
+}
+
+// ------------------------------------------------------------------ BWT + Occ
+// One warp per checkpoint block: gathers the block's BWT bytes, stores them, and
+// writes the block's per-row symbol counts into occ[row][blk+1] (prefix-summed
+// later, in place).
+__global__ void __launch_bounds__(256)
+    bwt_block_kernel(const uint8_t *__restrict__ text, const int32_t *__restrict__ sa, int64_t n,
+                     int occ_rate, const int32_t *__restrict__ row_of_code, int nrows,
+                     uint8_t *__restrict__ bwt, int32_t *__restrict__ occ, int64_t ncp, int64_t nblk)
+{
+    __shared__ int s_row[256];
+    s_row[threadIdx.x] = row_of_code[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t blk = warp_g; blk < nblk; blk += nwarps) {
+        int64_t j0 = blk * occ_rate;
+        int64_t j1 = j0 + occ_rate < n ? j0 + occ_rate : n;
+        for (int rg = 0; rg < nrows; rg += 8) {
+            int cnt[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) cnt[r] = 0;
+            for (int64_t j = j0 + lane; j < j1; j += 32) {
+                uint8_t c;
+                if (rg == 0) {
+                    int64_t p = (int64_t)__ldg(sa + j) - 1;
+                    if (p < 0) p += n;
+                    c = __ldg(text + p);
+                    bwt[j] = c;
+                } else {
+                    c = bwt[j];
+                }
+                int r = s_row[c] - rg;
+#pragma unroll
+                for (int q = 0; q < 8; q++) cnt[q] += (r == q);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                int v = cnt[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == q && rg + q < nrows) occ[(int64_t)(rg + q) * ncp + blk + 1] = v;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// In-place inclusive prefix sum of occ[row][1..nblk]; occ[row][0] = 0.  One block per row.
+__global__ void __launch_bounds__(1024) occ_scan_kernel(int32_t *__restrict__ occ, int64_t ncp, int64_t nblk)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    int32_t *row = occ + (int64_t)blockIdx.x * ncp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { row[0] = 0; s_carry = 0; }
+    __syncthreads();
+    constexpr int IT = 4;
+    for (int64_t base = 0; base < nblk; base += 1024 * IT) {
+        int v[IT], sum = 0;
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            int64_t i = base + (int64_t)tid * IT + k;
+            v[k] = i < nblk ? row[1 + i] : 0;
+            sum += v[k];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_w[lane];
+            int winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_w[lane] = winc - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        int carry = s_carry;
+        int run = carry + s_w[warp] + inc - sum;
+#pragma unroll
+        for (int k = 0; k < IT; k++) {
+            int64_t i = base + (int64_t)tid * IT + k;
+            run += v[k];
+            if (i < nblk) row[1 + i] = run;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = run;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ LCP
+// lcp[j] = LCP(suffix sa[j-1], suffix sa[j]) by direct comparison of bit-packed
+// windows (64 stream bits per step).  `slack` = 1 for the ACGT$ layout (the
+// sentinel shares a code with 'A', and being unique it can never match), else 0.
+__global__ void __launch_bounds__(256)
+    lcp_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ sa, int64_t n, int bits,
+               int slack, int32_t *__restrict__ lcp)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (j == 0) { lcp[0] = 0; return; }
+    int64_t a = __ldg(sa + j - 1), b = __ldg(sa + j);
+    int64_t limit = n - slack - (a > b ? a : b);
+    int64_t h = 0;
+    const int per = 64 / bits;
+    while (h < limit) {
+        uint64_t x = window64(packed, (a + h) * bits) ^ window64(packed, (b + h) * bits);
+        if (x) {
+            h += __clzll((long long)x) / bits;
+            break;
+        }
+        h += per;
+    }
+    lcp[j] = (int32_t)(h < limit ? h : limit);
+}
+
+}  // namespace bwtk
+
+using namespace bwtk;
+
+extern "C" int32_t bwtk_version(void) { return 100; }
+
+extern "C" int32_t bwtk_last_error(char *buf, int32_t buflen)
+{
+    if (!buf || buflen <= 0) return BWTK_EINVAL;
+    strncpy(buf, g_err, (size_t)buflen - 1);
+    buf[buflen - 1] = 0;
+    return BWTK_OK;
+}
+
+extern "C" int64_t bwtk_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int32_t bwtk_byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, void *stream)
+{
+    BWTK_REQUIRE(h_totals && n >= 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *scratch = nullptr;
+    BWTK_CUDA(cudaMallocAsync((void **)&scratch, 256 * sizeof(unsigned long long), st));
+    int rc = byte_histogram(d_text, n, h_totals, scratch, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+extern "C" int64_t bwtk_bwt_occ_workspace_bytes(int64_t, int32_t, int32_t) { return 4096; }
+
+extern "C" int32_t bwtk_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int32_t occ_rate,
+                                const int32_t *h_row_of_code, int32_t nrows, uint8_t *d_bwt,
+                                int32_t *d_occ, void *d_ws, int64_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return BWTK_OK;
+    BWTK_REQUIRE(d_text && d_sa && d_bwt && d_occ && d_ws && h_row_of_code, "null pointer");
+    BWTK_REQUIRE(occ_rate >= 1 && nrows >= 1 && nrows <= 256, "bad occ_rate/nrows");
+    BWTK_REQUIRE(ws_bytes >= 1024, "workspace too small");
+    int32_t *d_rows = (int32_t *)d_ws;
+    BWTK_CUDA(cudaMemcpyAsync(d_rows, h_row_of_code, 256 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    int64_t nblk = ceil_div(n, occ_rate);
+    int64_t ncp = n / occ_rate + 1 + (n % occ_rate != 0);
+    int64_t warps_needed = nblk;
+    int64_t grid = ceil_div(warps_needed, 8);
+    if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
+    bwt_block_kernel<<<(unsigned)grid, 256, 0, st>>>(d_text, d_sa, n, occ_rate, d_rows, nrows, d_bwt,
+                                                     d_occ, ncp, nblk);
+    BWTK_LAUNCH_CHECK();
+    occ_scan_kernel<<<nrows, 1024, 0, st>>>(d_occ, ncp, nblk);
+    BWTK_LAUNCH_CHECK();
+    BWTK_CUDA(cudaStreamSynchronize(st));  // h_row_of_code is caller memory
+    return BWTK_OK;
+}
+
+extern "C" int64_t bwtk_lcp_workspace_bytes(int64_t n)
+{
+    if (n < 1) n = 1;
+    return align_up(packed_words(n, 8) * 4, 256) + 8192;
+}
+
+extern "C" int32_t bwtk_lcp_build(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int32_t *d_lcp,
+                                  void *d_ws, int64_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return BWTK_OK;
+    BWTK_REQUIRE(d_text && d_sa && d_lcp && d_ws, "null pointer");
+    if (ws_bytes < bwtk_lcp_workspace_bytes(n)) {
+        set_error("lcp workspace: need %lld bytes", (long long)bwtk_lcp_workspace_bytes(n));
+        return BWTK_EWORKSPACE;
+    }
+    Carver c(d_ws, ws_bytes);
+    uint32_t *packed = c.take<uint32_t>(packed_words(n, 8));
+    uint8_t *d_lut = c.take<uint8_t>(256);
+    unsigned long long *d_hist = c.take<unsigned long long>(256);
+    int64_t totals[256];
+    int rc = byte_histogram(d_text, n, totals, d_hist, st);
+    if (rc) return rc;
+    uint8_t lut[256];
+    bool fast;
+    int bits = choose_packing(d_text, n, totals, lut, &fast, st);
+    if (bits < 0) { set_error("choose_packing failed"); return BWTK_ECUDA; }
+    rc = pack_text(d_text, n, lut, bits, packed, d_lut, st);
+    if (rc) return rc;
+    lcp_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(packed, d_sa, n, bits, fast ? 1 : 0, d_lcp);
+    BWTK_LAUNCH_CHECK();
+    return BWTK_OK;
+}

@@ -1,0 +1,195 @@
+"""Device-resident FM index of one contig: the arrays behind ``BWTCore``.
+
+Layout in HBM (all torch tensors on one CUDA device):
+  text   uint8[n]      the text bytes (with the caller's '$')
+  sa     int32[n]      suffix array            (bwt.py:212-264)
+  isa    int32[n]      inverse suffix array    (by-product of prefix doubling)
+  bwt    uint8[n]      BWT bytes               (bwt.py:266-274)
+  occ    int32[σ][ncp] checkpoints every occ_rate symbols (bwt.py:288-326)
+  C/tot  int64[256]    FM "C" array / totals   (bwt.py:276-286)
+  lcp    int32[n]      LCP array, built on demand (bwt.py:55-72)
+  kmer   int32[65537] bucket offsets + int32[R] positions (bwt.py:138-171)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+class DeviceIndex:
+    def __init__(self, text, occ_rate: int = 128, device=None, build_kmer: bool = True,
+                 text_is_device: bool = False):
+        torch = _torch()
+        self.torch = torch
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.occ_rate = int(occ_rate)
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            if text_is_device:
+                self.text = text
+            else:
+                if isinstance(text, str):
+                    text = text.encode("utf-8")
+                if isinstance(text, (bytes, bytearray, memoryview)):
+                    host = np.frombuffer(text, dtype=np.uint8)
+                else:
+                    host = np.ascontiguousarray(text, dtype=np.uint8)
+                self.text = torch.from_numpy(host.copy() if host.size else np.zeros(0, np.uint8)).to(self.device)
+            n = int(self.text.numel())
+            self.n = n
+            st = _lib.stream_ptr()
+            # a5: C array
+            totals = np.zeros(256, np.int64)
+            if n:
+                _lib.check(L.bwtk_byte_histogram(self.text.data_ptr(), n, totals.ctypes.data, st), "byte_histogram")
+            self.totals = totals
+            counts = np.zeros(256, np.int64)
+            cum = 0
+            for b in range(256):
+                counts[b] = cum
+                cum += int(totals[b])
+            self.counts = counts
+            codes = [b for b in range(256) if totals[b] > 0]
+            self.codes = codes
+            row = np.full(256, -1, np.int32)
+            for r, b in enumerate(codes):
+                row[b] = r
+            self.row_of_code = row
+            self.d_C = torch.from_numpy(counts).to(self.device)
+            self.d_tot = torch.from_numpy(totals).to(self.device)
+            self.d_row = torch.from_numpy(row).to(self.device)
+            # a3: suffix array (+ inverse)
+            self.sa = torch.empty(n, dtype=torch.int32, device=self.device)
+            self.isa = torch.empty(n, dtype=torch.int32, device=self.device)
+            self.sa_stats = np.zeros(8, np.int64)
+            if n:
+                wsb = int(L.bwtk_sa_workspace_bytes(n))
+                ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+                _lib.check(L.bwtk_sa_build(self.text.data_ptr(), n, self.sa.data_ptr(), self.isa.data_ptr(),
+                                           ws.data_ptr(), wsb, self.sa_stats.ctypes.data, st), "sa_build")
+                del ws
+            # a4 + a6: BWT and Occ checkpoints
+            self.ncp = (n // self.occ_rate + 1 + (1 if n % self.occ_rate else 0)) if n else 0
+            nrows = max(len(codes), 1)
+            self.bwt = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self.occ = torch.zeros((nrows, max(self.ncp, 1)), dtype=torch.int32, device=self.device)
+            if n:
+                wsb = int(L.bwtk_bwt_occ_workspace_bytes(n, self.occ_rate, nrows))
+                ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+                _lib.check(L.bwtk_bwt_occ(self.text.data_ptr(), self.sa.data_ptr(), n, self.occ_rate,
+                                          row.ctypes.data, len(codes), self.bwt.data_ptr(), self.occ.data_ptr(),
+                                          ws.data_ptr(), wsb, st), "bwt_occ")
+            self._lcp = None
+            # a2: 8-mer index
+            self.kmer_off = None
+            self.kmer_pos = None
+            self.kmer_count = 0
+            if build_kmer:
+                self.build_kmer()
+
+    # ------------------------------------------------------------------ a2
+    def build_kmer(self):
+        torch, L, n = self.torch, _lib.lib(), self.n
+        with torch.cuda.device(self.device):
+            self.kmer_off = torch.zeros(65537, dtype=torch.int32, device=self.device)
+            self.kmer_pos = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+            cnt = C.c_int64(0)
+            if n >= 8:
+                wsb = int(L.bwtk_kmer8_workspace_bytes(n))
+                ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+                _lib.check(L.bwtk_kmer8_index(self.text.data_ptr(), n, self.kmer_off.data_ptr(),
+                                              self.kmer_pos.data_ptr(), C.addressof(cnt), ws.data_ptr(), wsb,
+                                              _lib.stream_ptr()), "kmer8_index")
+            self.kmer_count = int(cnt.value)
+            self.kmer_pos = self.kmer_pos[: self.kmer_count]
+            self._kmer_off_host = None
+
+    def kmer_bucket(self, code: int) -> np.ndarray:
+        if self._kmer_off_host is None:
+            self._kmer_off_host = self.kmer_off.cpu().numpy()
+        lo, hi = int(self._kmer_off_host[code]), int(self._kmer_off_host[code + 1])
+        if hi <= lo:
+            return np.zeros(0, np.int32)
+        return self.kmer_pos[lo:hi].cpu().numpy()
+
+    # ------------------------------------------------------------------ a10
+    @property
+    def lcp(self):
+        if self._lcp is None:
+            torch, L, n = self.torch, _lib.lib(), self.n
+            with torch.cuda.device(self.device):
+                self._lcp = torch.empty(n, dtype=torch.int32, device=self.device)
+                if n:
+                    wsb = int(L.bwtk_lcp_workspace_bytes(n))
+                    ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+                    _lib.check(L.bwtk_lcp_build(self.text.data_ptr(), self.sa.data_ptr(), n, self._lcp.data_ptr(),
+                                                ws.data_ptr(), wsb, _lib.stream_ptr()), "lcp_build")
+        return self._lcp
+
+    # ------------------------------------------------------------------ a8 / a9
+    def search_device(self, d_pats, stride: int, d_lens, nq: int):
+        torch, L = self.torch, _lib.lib()
+        with torch.cuda.device(self.device):
+            sp = torch.empty(nq, dtype=torch.int32, device=self.device)
+            ep = torch.empty(nq, dtype=torch.int32, device=self.device)
+            _lib.check(L.bwtk_bsearch_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
+                                            self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
+                                            self.d_row.data_ptr(), self.n, _lib.ptr(d_pats), stride,
+                                            d_lens.data_ptr(), nq, sp.data_ptr(), ep.data_ptr(),
+                                            _lib.stream_ptr()), "bsearch_batch")
+        return sp, ep
+
+    def backward_search_batch(self, patterns: Sequence) -> Tuple[np.ndarray, np.ndarray]:
+        """Inclusive (sp, ep) for every pattern (bytes/str); (-1,-1) when absent."""
+        torch = self.torch
+        nq = len(patterns)
+        if nq == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
+        bs = [p.encode("utf-8") if isinstance(p, str) else bytes(p) for p in patterns]
+        stride = max(1, max(len(b) for b in bs))
+        mat = np.zeros((nq, stride), np.uint8)
+        lens = np.zeros(nq, np.int32)
+        for i, b in enumerate(bs):
+            lens[i] = len(b)
+            if b:
+                mat[i, : len(b)] = np.frombuffer(b, np.uint8)
+        d_p = torch.from_numpy(mat).to(self.device)
+        d_l = torch.from_numpy(lens).to(self.device)
+        sp, ep = self.search_device(d_p, stride, d_l, nq)
+        return sp.cpu().numpy(), ep.cpu().numpy()
+
+    def motif_sweep(self, kmax: int = 10):
+        """(sp, ep) device tensors for every ACGT motif of length 1..kmax, index
+        (4^k-4)/3 + base-4 value (first character most significant)."""
+        torch, L = self.torch, _lib.lib()
+        total = (4 ** (kmax + 1) - 4) // 3
+        with torch.cuda.device(self.device):
+            sp = torch.empty(total, dtype=torch.int32, device=self.device)
+            ep = torch.empty(total, dtype=torch.int32, device=self.device)
+            _lib.check(L.bwtk_bsearch_motif_sweep(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
+                                                  self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
+                                                  self.d_row.data_ptr(), self.n, kmax, sp.data_ptr(),
+                                                  ep.data_ptr(), _lib.stream_ptr()), "motif_sweep")
+        return sp, ep
+
+    def rank_batch(self, codes: Sequence[int], positions: Sequence[int]) -> np.ndarray:
+        torch, L = self.torch, _lib.lib()
+        nq = len(codes)
+        if nq == 0:
+            return np.zeros(0, np.int64)
+        with torch.cuda.device(self.device):
+            d_c = torch.tensor(list(codes), dtype=torch.int32, device=self.device)
+            d_p = torch.tensor(list(positions), dtype=torch.int64, device=self.device)
+            out = torch.empty(nq, dtype=torch.int64, device=self.device)
+            _lib.check(L.bwtk_rank_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
+                                         self.occ_rate, self.d_row.data_ptr(), self.n, d_c.data_ptr(),
+                                         d_p.data_ptr(), nq, out.data_ptr(), _lib.stream_ptr()), "rank_batch")
+        return out.cpu().numpy()

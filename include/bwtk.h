@@ -1,0 +1,166 @@
+/*
+ * bwtk.h -- C ABI of libbwtk.so: the sm_100a kernels under the `bwt` module.
+ *
+ * The reference (wyim-pgl/bwt-algorithm, bwt.py) is pure Python and has no
+ * FFI; the drop-in boundary is its Python module surface.
+ * This header is the new seam UNDER those Python names: every entry point
+ * below names the reference method (file:line) whose arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would
+ * add to call them.
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller (the
+ *    Python side allocates with torch); the library never returns memory it
+ *    allocated and keeps no global state except a thread-local error string.
+ *  - h_* pointers are HOST pointers (small outputs the call synchronises for).
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream).
+ *  - return value: 0 = OK, negative = BWTK_E*; on error outputs are undefined
+ *    and bwtk_last_error() describes the failure.
+ *  - record capacity overflow returns BWTK_EOVERFLOW with the required count
+ *    in the count slot; results are deterministic, so the caller re-allocates
+ *    and calls again.
+ *  - n < 2^30 for every text (int32 suffix arrays as in the reference).
+ */
+#ifndef BWTK_H
+#define BWTK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BWTK_OK 0
+#define BWTK_EINVAL (-1)
+#define BWTK_ECUDA (-2)
+#define BWTK_EWORKSPACE (-3)
+#define BWTK_EOVERFLOW (-4)
+#define BWTK_EINTERNAL (-5)
+
+#define BWTK_REC_W 8 /* int32 per record row: start,end,period,copies,total_mm,max_mm,aux0,aux1 */
+
+int32_t bwtk_version(void);
+/* copies the calling thread's last error message (NUL terminated) */
+int32_t bwtk_last_error(char *buf, int32_t buflen);
+/* number of kernels this library has launched in the calling process */
+int64_t bwtk_launch_count(void);
+
+/* ---- a5: BWTCore._build_char_counts (bwt.py:276-286) ------------------
+ * byte histogram of the text; h_totals[256] (host) receives the counts.
+ * The exclusive prefix sum over present bytes (the FM "C" array) is a 256-entry
+ * host loop done by the caller.  Synchronises the stream. */
+int32_t bwtk_byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, void *stream);
+
+/* ---- a3: BWTCore._build_suffix_array (bwt.py:212-264) -----------------
+ * suffix array under byte order, shorter suffix first (key2 = -1 rule).
+ * d_isa_out may be NULL; otherwise receives the inverse suffix array.
+ * h_stats (may be NULL) receives int64[8]: rounds, bits/symbol, symbols/key,
+ * active after round 0, sum of active over rounds, radix passes, 0, 0.
+ * Synchronises the stream (one 4-byte read-back per doubling round). */
+int64_t bwtk_sa_workspace_bytes(int64_t n);
+int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa, int32_t *d_isa_out,
+                      void *d_ws, int64_t ws_bytes, int64_t *h_stats, void *stream);
+
+/* ---- a4+a6: _build_bwt_array + _build_occurrence_checkpoints ----------
+ * (bwt.py:266-274, 288-326).  d_bwt[i] = text[(sa[i]-1) mod n].
+ * h_row_of_code[256]: row index in d_occ for each byte value, -1 if the byte
+ * does not occur.  d_occ is [nrows][ncp] int32 row-major with
+ * ncp = n/occ_rate + 1 + (n%occ_rate != 0): cp[0]=0, cp[m+1]=#code in
+ * bwt[0:(m+1)*occ_rate], plus the total when the last block is partial.
+ * d_ws needs bwtk_bwt_occ_workspace_bytes(n, occ_rate, nrows) bytes. */
+int64_t bwtk_bwt_occ_workspace_bytes(int64_t n, int32_t occ_rate, int32_t nrows);
+int32_t bwtk_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int32_t occ_rate,
+                     const int32_t *h_row_of_code, int32_t nrows, uint8_t *d_bwt, int32_t *d_occ,
+                     void *d_ws, int64_t ws_bytes, void *stream);
+
+/* ---- a10: _kasai_lcp_uint8 (bwt.py:55-72) ------------------------------
+ * lcp[0]=0, lcp[r]=LCP(text[sa[r-1]:], text[sa[r]:]). */
+int64_t bwtk_lcp_workspace_bytes(int64_t n);
+int32_t bwtk_lcp_build(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int32_t *d_lcp,
+                       void *d_ws, int64_t ws_bytes, void *stream);
+
+/* ---- a2: _build_kmer_hash(k=8) (bwt.py:138-171) -------------------------
+ * d_bucket_off[65537]: start of each 16-bit code's bucket in d_pos;
+ * d_pos: window start positions, ascending inside a bucket.  *h_count receives
+ * the number of recorded windows (0 when n < 8).  Synchronises. */
+int64_t bwtk_kmer8_workspace_bytes(int64_t n);
+int32_t bwtk_kmer8_index(const uint8_t *d_text, int64_t n, int32_t *d_bucket_off, int32_t *d_pos,
+                         int64_t *h_count, void *d_ws, int64_t ws_bytes, void *stream);
+
+/* ---- a8/a9: rank + backward_search (bwt.py:335-389) ---------------------
+ * Batched: pattern q is d_pats[q*stride : q*stride+d_lens[q]] (bytes).
+ * d_C[256]/d_tot[256]: C array / totals (int64), d_row_of_code[256] int32.
+ * Outputs inclusive (sp,ep), (-1,-1) if absent, (0,n-1) for an empty pattern. */
+int32_t bwtk_bsearch_batch(const uint8_t *d_bwt, const int32_t *d_occ, int64_t ncp, int32_t occ_rate,
+                           const int64_t *d_C, const int64_t *d_tot, const int32_t *d_row_of_code,
+                           int64_t n, const uint8_t *d_pats, int64_t stride, const int32_t *d_lens,
+                           int64_t nq, int32_t *d_sp, int32_t *d_ep, void *stream);
+/* Trie sweep over every ACGT motif of length 1..kmax (kmax <= 12).  Motif m of
+ * length k with base-4 value v (first character most significant) is stored
+ * at index (4^k - 4)/3 + v.  One LF step per motif. */
+int32_t bwtk_bsearch_motif_sweep(const uint8_t *d_bwt, const int32_t *d_occ, int64_t ncp,
+                                 int32_t occ_rate, const int64_t *d_C, const int64_t *d_tot,
+                                 const int32_t *d_row_of_code, int64_t n, int32_t kmax,
+                                 int32_t *d_sp, int32_t *d_ep, void *stream);
+/* rank(code,pos) probes (bwt.py:335-357) */
+int32_t bwtk_rank_batch(const uint8_t *d_bwt, const int32_t *d_occ, int64_t ncp, int32_t occ_rate,
+                        const int32_t *d_row_of_code, int64_t n, const int32_t *d_codes,
+                        const int64_t *d_pos, int64_t nq, int64_t *d_out, void *stream);
+
+/* ---- a12: Tier1STRFinder._find_simple_tandems_kmer (bwt.py:1426-1531) ---
+ * rows: start,end,motif_len,copies,0,0,0,0 in the reference's emission order.
+ * d_seen_out (may be NULL): n bytes, the final seen mask. */
+int64_t bwtk_tier1_workspace_bytes(int64_t n);
+int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max_motif_len, int32_t min_copies,
+                        int32_t min_array_len, double min_entropy, int32_t *d_rec, int64_t cap,
+                        int64_t *h_count, uint8_t *d_seen_out, void *d_ws, int64_t ws_bytes,
+                        void *stream);
+
+/* ---- a13: Tier2LCPFinder.find_long_unit_repeats_strict (bwt.py:1891-2001)
+ * rows: start,end,primitive_period,copies,0,0,unit_len,0, ordered by unit
+ * length descending then start ascending (the reference's order). */
+int64_t bwtk_strict_workspace_bytes(int64_t n, int64_t max_unit_len);
+int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n, int64_t min_unit_len, int64_t max_unit_len,
+                         int64_t max_mismatch, int64_t min_copies, int32_t *d_rec, int64_t cap,
+                         int64_t *h_count, void *d_ws, int64_t ws_bytes, void *stream);
+
+/* ---- a15: _detect_lcp_plateaus (bwt.py:2118-2145, 2500-2560) ------------
+ * rows: start,end,period(=threshold),copies,0,0,0,0; *h_threshold = -1 when
+ * no scan happens (max LCP < min_period). */
+int64_t bwtk_plateau_workspace_bytes(int64_t n);
+int32_t bwtk_lcp_plateaus(const uint8_t *d_text, int64_t n_text, const int32_t *d_sa,
+                          const int32_t *d_lcp, int64_t n, int64_t min_period, int64_t max_period,
+                          int64_t min_copies, int32_t *d_rec, int64_t cap, int64_t *h_count,
+                          int64_t *h_threshold, void *d_ws, int64_t ws_bytes, void *stream);
+
+/* ---- a16/a14/a17: extension + consensus batches --------------------------
+ * mode 0: _extend_with_mismatches (bwt.py:2392-2498), out row int32[8]:
+ *         array_start,array_end,copies,full_start,full_end,0,0,0;
+ *         d_flags[i] bit0 = allow_mismatches.
+ * mode 1: _extend_tandem_fm (bwt.py:2697-2805), out row: start,end,copies,... */
+int32_t bwtk_extend_batch(const uint8_t *d_text, int64_t n, const int32_t *d_seed,
+                          const int32_t *d_period, const int32_t *d_flags, int64_t m, int32_t mode,
+                          int32_t *d_out, void *stream);
+/* MotifUtils.build_consensus_motif_array (bwt.py:1207-1256): consensus bytes
+ * for item i at d_cons[d_cons_off[i] : +period]; d_mm row int32[4]:
+ * total_mm, max_mm_per_copy, copies_used, 0. */
+int32_t bwtk_consensus_batch(const uint8_t *d_text, int64_t text_size, const int32_t *d_start,
+                             const int32_t *d_period, const int32_t *d_copies,
+                             const int64_t *d_cons_off, int64_t m, uint8_t *d_cons, int32_t *d_mm,
+                             void *stream);
+
+/* ---- a16: _find_repeats_simple (bwt.py:2177-2390), clock frozen ----------
+ * rows: array_start,array_end,p_eff,copies_full,total_mm,max_mm,cons_start,
+ * copies_used, before the host-side (start,end,canonical) dedup.
+ * d_plogp: (max_p+1)^2 doubles, plogp[c*(max_p+1)+L] = (c/L)*log2(c/L) as the
+ * host computes it (keeps the entropy gate bit-identical to numpy's). */
+int32_t bwtk_period_scan(const uint8_t *d_text, int64_t n, int64_t min_period, int64_t max_period,
+                         int32_t allow_mismatches, int64_t min_copies, int64_t min_array_len,
+                         double min_entropy, const uint8_t *d_tier1_mask, const double *d_plogp,
+                         int64_t plogp_dim, int32_t *d_rec, int64_t cap, int64_t *h_count,
+                         int64_t *h_iterations, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BWTK_H */

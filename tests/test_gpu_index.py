@@ -1,0 +1,136 @@
+"""GPU parity of the index arrays against the CPU oracle.
+
+Bit-exact bar: suffix array, inverse SA, BWT, C array, Occ checkpoints, LCP,
+8-mer table, rank and backward-search intervals.
+"""
+import numpy as np
+import pytest
+
+from tests.util import gen_contig, text_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def DeviceIndex():
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200.device_index import DeviceIndex as D
+
+    return D
+
+
+def _check_index(DeviceIndex, oracle, text: bytes, occ_rate=128, searches=True):
+    ix = DeviceIndex(text, occ_rate=occ_rate)
+    oi = oracle.OracleIndex(text, occ_rate=occ_rate)
+    n = len(text)
+    assert ix.n == n
+    sa = ix.sa.cpu().numpy()
+    assert sa.dtype == np.int32
+    assert np.array_equal(sa, oi.sa), f"SA differs (n={n})"
+    isa = ix.isa.cpu().numpy()
+    inv = np.empty(n, np.int32)
+    inv[oi.sa] = np.arange(n, dtype=np.int32)
+    assert np.array_equal(isa, inv), "ISA differs"
+    assert np.array_equal(ix.bwt.cpu().numpy(), oi.bwt), "BWT differs"
+    assert np.array_equal(ix.totals, oi.totals)
+    present = oi.totals > 0
+    assert np.array_equal(ix.counts[present], oi.counts[present])
+    occ = ix.occ.cpu().numpy()
+    for code, cp in oi.occ.items():
+        r = ix.row_of_code[code]
+        assert r >= 0
+        assert np.array_equal(occ[r, : cp.size], cp), f"Occ differs for code {code}"
+    assert np.array_equal(ix.lcp.cpu().numpy(), oi.lcp()), "LCP differs"
+    # k-mer table
+    codes, pos = oracle.kmer8_pairs(text)
+    order = np.argsort(codes, kind="stable")
+    assert ix.kmer_count == codes.size
+    assert np.array_equal(ix.kmer_pos.cpu().numpy(), pos[order])
+    off = ix.kmer_off.cpu().numpy()
+    assert off[65536] == codes.size
+    if codes.size:
+        hist = np.bincount(codes, minlength=65536)
+        assert np.array_equal(np.diff(off), hist)
+    if searches and n:
+        rng = np.random.default_rng(n)
+        pats = [b""]
+        for k in range(1, 4):
+            for v in range(4 ** k):
+                pats.append(bytes(b"ACGT"[(v >> (2 * (k - 1 - j))) & 3] for j in range(k)))
+        pats += [b"N", b"AN", b"$", b"A$", b"X", b"AXA", b"acgt"]
+        for L in (5, 8, 10, 13):
+            for _ in range(30):
+                pats.append(bytes(b"ACGT"[x] for x in rng.integers(0, 4, L)))
+        for _ in range(60):
+            L = int(rng.integers(1, min(14, n) + 1))
+            p = int(rng.integers(0, n - L + 1))
+            pats.append(text[p:p + L])
+        sp, ep = ix.backward_search_batch(pats)
+        stride = max(len(p) for p in pats)
+        mat = np.zeros((len(pats), stride), np.uint8)
+        lens = np.array([len(p) for p in pats], np.int32)
+        for i, p in enumerate(pats):
+            mat[i, : len(p)] = np.frombuffer(p, np.uint8)
+        osp, oep = oi.backward_search_batch(mat, lens)
+        assert np.array_equal(sp.astype(np.int64), osp), "backward_search sp differs"
+        assert np.array_equal(ep.astype(np.int64), oep), "backward_search ep differs"
+    return ix, oi
+
+
+@pytest.mark.parametrize("name,text", text_cases())
+def test_index_small_cases(DeviceIndex, oracle, name, text):
+    _check_index(DeviceIndex, oracle, text)
+
+
+@pytest.mark.parametrize("occ_rate", [1, 7, 64, 100, 256])
+def test_index_occ_rates(DeviceIndex, oracle, occ_rate):
+    text = gen_contig(3000, 11).tobytes() + b"$"
+    _check_index(DeviceIndex, oracle, text, occ_rate=occ_rate)
+
+
+@pytest.mark.parametrize("n,seed", [(150_000, 42), (1_000_003, 7)])
+def test_index_planted_contigs(DeviceIndex, oracle, n, seed):
+    text = gen_contig(n, seed).tobytes() + b"$"
+    ix, oi = _check_index(DeviceIndex, oracle, text)
+    assert ix.sa_stats[6] == 1  # ACGT$ fast path
+
+
+def test_index_with_N_block_100k(DeviceIndex, oracle):
+    s = gen_contig(100_000, 5)
+    s[40_000:52_000] = ord("N")
+    _check_index(DeviceIndex, oracle, s.tobytes() + b"$")
+
+
+def test_motif_sweep_matches_batched_search(DeviceIndex, oracle):
+    text = gen_contig(200_000, 3).tobytes() + b"$"
+    ix = DeviceIndex(text, build_kmer=False)
+    kmax = 6
+    sp, ep = ix.motif_sweep(kmax)
+    sp, ep = sp.cpu().numpy(), ep.cpu().numpy()
+    pats = []
+    for k in range(1, kmax + 1):
+        for v in range(4 ** k):
+            pats.append(bytes(b"ACGT"[(v >> (2 * (k - 1 - j))) & 3] for j in range(k)))
+    bsp, bep = ix.backward_search_batch(pats)
+    assert np.array_equal(sp, bsp) and np.array_equal(ep, bep)
+    oi = oracle.OracleIndex(text)
+    mat = np.zeros((len(pats), kmax), np.uint8)
+    lens = np.array([len(p) for p in pats], np.int32)
+    for i, p in enumerate(pats):
+        mat[i, : len(p)] = np.frombuffer(p, np.uint8)
+    osp, oep = oi.backward_search_batch(mat, lens)
+    assert np.array_equal(sp.astype(np.int64), osp) and np.array_equal(ep.astype(np.int64), oep)
+
+
+def test_rank_probes(DeviceIndex, oracle):
+    text = gen_contig(5000, 2).tobytes() + b"$"
+    ix = DeviceIndex(text, build_kmer=False)
+    oi = oracle.OracleIndex(text)
+    rng = np.random.default_rng(0)
+    codes = [int(x) for x in rng.choice([36, 65, 67, 71, 84, 78, 0, 255], 500)]
+    pos = [int(x) for x in rng.integers(-3, len(text) + 4, 500)]
+    got = ix.rank_batch(codes, pos)
+    for c, p, g in zip(codes, pos, got):
+        pp = min(max(p, 0), len(text))
+        want = int(np.count_nonzero(oi.bwt[:pp] == c))
+        assert g == want
