@@ -28,7 +28,7 @@ __device__ __forceinline__ int base_bits(uint8_t c)
 
 struct CountValid {
     const uint8_t *text;
-    __device__ uint32_t operator()(int64_t i) const { return base_bits(__ldg(text + i)) >= 0 ? 1u : 0u; }
+    __device__ uint64_t operator()(int64_t i) const { return base_bits(__ldg(text + i)) >= 0 ? 1ull : 0ull; }
 };
 
 struct EmitValid {
@@ -36,9 +36,10 @@ struct EmitValid {
     uint8_t *cc;      // compacted 2-bit codes of the valid symbols
     int32_t *pos;     // recorded window positions, in recording order
     uint32_t *vend;   // number of valid symbols up to and including the window's last symbol
-    __device__ void operator()(int64_t i, uint32_t excl, uint32_t cnt) const
+    __device__ void operator()(int64_t i, uint64_t excl64, uint64_t cnt) const
     {
         if (!cnt) return;
+        uint32_t excl = (uint32_t)excl64;
         cc[excl] = (uint8_t)base_bits(__ldg(text + i));
         if (i < 7) return;
         // V7 = valid symbols among text[0..7]

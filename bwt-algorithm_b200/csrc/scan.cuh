@@ -3,8 +3,9 @@
 // chain through a decoupled look-back over 64-bit status words, so input and
 // output are each touched once.
 //
-//   Count  : __device__ uint32_t operator()(int64_t i)            (items at i)
-//   Emit   : __device__ void operator()(int64_t i, uint32_t excl, uint32_t cnt)
+//   Count  : __device__ uint64_t operator()(int64_t i)            (items at i)
+//   Emit   : __device__ void operator()(int64_t i, uint64_t excl, uint64_t cnt)
+// Counts are summed in 62 bits, so two 31-bit counters may be packed in one value.
 #pragma once
 #include "common.cuh"
 
@@ -51,12 +52,12 @@ __global__ void __launch_bounds__(THREADS)
     __syncthreads();
     const int64_t tile = s_tile;
     const int64_t i0 = tile * TILE + (int64_t)tid * ITEMS;
-    uint32_t c[ITEMS];
+    unsigned long long c[ITEMS];
     unsigned long long sum = 0;
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         int64_t i = i0 + k;
-        c[k] = i < n ? count(i) : 0u;
+        c[k] = i < n ? (unsigned long long)count(i) : 0ull;
         sum += c[k];
     }
     unsigned long long inc = sum;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         int64_t i = i0 + k;
-        if (i < n) emit(i, (uint32_t)run, c[k]);
+        if (i < n) emit(i, run, c[k]);
         run += c[k];
     }
 }

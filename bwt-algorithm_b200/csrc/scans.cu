@@ -1,10 +1,848 @@
-// scans.cu -- detectors (placeholder until the kernels land)
-#include "common.cuh"
+// scans.cu -- the perfect-repeat detectors as parallel scans + ordered resolves.
+//
+//  * strict adjacency scan  (Tier2LCPFinder.find_long_unit_repeats_strict,
+//    reference bwt.py:1891-2001; the only detector the CLI runs)
+//  * Tier 1 sliding window  (Tier1STRFinder._find_simple_tandems_kmer,
+//    reference bwt.py:1426-1531)
+//  * LCP plateaus           (Tier2LCPFinder._detect_lcp_plateaus and
+//    _analyze_sa_interval_for_tandems, reference bwt.py:2118-2145, 2500-2560)
+//
+// The reference walks the text greedily (emit, jump past the array, otherwise
+// step).  Here every kernel first computes the position-independent facts in
+// parallel (maximal runs of text[j]==text[j+u]; "would emit if visited"
+// candidates), and the greedy order is then replayed over the sparse candidate
+// list only: a short dependency-chain walk for the strict scan, pointer jumping
+// over the candidate successor graph for Tier 1 (which also reproduces the
+// reference's adaptive position_step sampling exactly).
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace bwtk {
+
+// ===========================================================================
+// strict adjacency scan
+// ===========================================================================
+namespace strict {
+
+constexpr int TP = 8192;       // positions per CTA tile
+constexpr int THREADS = 256;   // 8 warps x 1024 positions
+
+struct CandOut {
+    unsigned long long *key;   // ((umax - u) << abits) | run_start
+    uint32_t *val;             // run_end
+    unsigned long long *count;
+    int64_t cap;
+    int abits;
+    int64_t umax;
+};
+
+__device__ __forceinline__ void push_cand(const CandOut &o, int64_t u, int64_t a, int64_t b)
+{
+    unsigned long long slot = atomicAdd(o.count, 1ull);
+    if ((int64_t)slot < o.cap) {
+        o.key[slot] = ((unsigned long long)(o.umax - u) << o.abits) | (unsigned long long)a;
+        o.val[slot] = (uint32_t)b;
+    }
+}
+
+// Units whose minimum run (mc-1)*u is >= 8 positions: a qualifying run then
+// contains at least one aligned group of 4 matching positions, so one 4-byte
+// compare per lane + a ballot filters 128 positions per warp step.
+__global__ void __launch_bounds__(THREADS)
+    find_runs_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t u_lo, int64_t u_hi,
+                     int64_t u_per_block, int64_t mc, CandOut out)
+{
+    extern __shared__ __align__(16) uint8_t s_text[];
+    const int64_t t0 = (int64_t)blockIdx.x * TP;
+    const int64_t ua = u_lo + (int64_t)blockIdx.y * u_per_block;
+    int64_t ub = ua + u_per_block - 1;
+    if (ub > u_hi) ub = u_hi;
+    if (ua > ub) return;
+    const int span = TP + (int)ub + 8;
+    for (int i = threadIdx.x * 4; i < span; i += THREADS * 4) {
+        uint32_t w = 0;
+        int64_t g = t0 + i;
+        if (g + 3 < n) {
+            w = (uint32_t)__ldg(text + g) | ((uint32_t)__ldg(text + g + 1) << 8) |
+                ((uint32_t)__ldg(text + g + 2) << 16) | ((uint32_t)__ldg(text + g + 3) << 24);
+        } else {
+            for (int q = 0; q < 4; q++)
+                if (g + q < n) w |= (uint32_t)__ldg(text + g + q) << (8 * q);
+        }
+        *reinterpret_cast<uint32_t *>(s_text + i) = w;
+    }
+    __syncthreads();
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s_text);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t base[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) base[c] = s32[(warp * 1024 + c * 128 + 4 * lane) >> 2];
+    for (int64_t u = ua; u <= ub; u++) {
+        const int64_t L = (mc - 1) * u;
+        const int64_t lim = n - u;  // E_u[j] defined for j < lim
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int loc = warp * 1024 + c * 128 + 4 * lane;
+            const int off = loc + (int)u;
+            uint32_t a = s32[off >> 2], b = s32[(off >> 2) + 1];
+            uint32_t sh = __funnelshift_r(a, b, (off & 3) * 8);
+            const int64_t pos = t0 + loc;
+            bool ok = (sh == base[c]) && (pos + 3 < lim);
+            unsigned B = __ballot_sync(0xffffffffu, ok);
+            if (B == 0) continue;
+            bool prev_ok = __shfl_up_sync(0xffffffffu, ok, 1);
+            if (lane == 0) {
+                prev_ok = false;
+                if (pos >= 4) {
+                    prev_ok = true;
+                    for (int q = 1; q <= 4; q++)
+                        if (__ldg(text + pos - q) != __ldg(text + pos - q + u)) { prev_ok = false; break; }
+                }
+            }
+            if (ok && !prev_ok) {
+                // streak of full groups starting at this lane
+                unsigned rest = ~(B >> lane);
+                int g = rest ? (__ffs(rest) - 1) : 32;
+                if (g > 32 - lane) g = 32 - lane;
+                bool ends_here = (lane + g) < 32;
+                if (!ends_here || (int64_t)4 * g + 6 >= L) {
+                    int64_t ra = pos;
+                    while (ra > 0 && __ldg(text + ra - 1) == __ldg(text + ra - 1 + u)) ra--;
+                    int64_t rb = pos + 4 * g;
+                    while (rb < lim && __ldg(text + rb) == __ldg(text + rb + u)) rb++;
+                    if (rb - ra >= L) push_cand(out, u, ra, rb);
+                }
+            }
+        }
+    }
+}
+
+// Units with (mc-1)*u < 8: one thread per position, run starts found directly.
+__global__ void __launch_bounds__(256)
+    find_runs_small_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t u_lo, int64_t u_hi,
+                           int64_t mc, CandOut out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t ci = __ldg(text + i);
+    for (int64_t u = u_lo; u <= u_hi; u++) {
+        int64_t lim = n - u;
+        if (i >= lim) break;
+        if (ci != __ldg(text + i + u)) continue;
+        if (i > 0 && __ldg(text + i - 1) == __ldg(text + i - 1 + u)) continue;  // not a run start
+        int64_t b = i + 1;
+        while (b < lim && __ldg(text + b) == __ldg(text + b + u)) b++;
+        if (b - i >= (mc - 1) * u) push_cand(out, u, i, b);
+    }
+}
+
+struct Resolved {
+    uint8_t *emit;       // per candidate
+    int32_t *row;        // per candidate, REC_W ints
+};
+
+// Replays the greedy walk over the sorted candidate runs of one unit length:
+// entry e = max(run start, end of the previous emission); emit when
+// e <= run_end - (mc-1)*u; the array then ends at e + u*(1 + (run_end-e)/u).
+__global__ void __launch_bounds__(256)
+    resolve_kernel(const uint8_t *__restrict__ text, const unsigned long long *__restrict__ key,
+                   const uint32_t *__restrict__ val, int64_t m, int abits, int64_t umax, int64_t mc,
+                   Resolved res)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const unsigned long long amask = (1ull << abits) - 1ull;
+    const unsigned long long kt = key[t];
+    const int64_t urev = (int64_t)(kt >> abits);
+    const int64_t u = umax - urev;
+    const int64_t L = (mc - 1) * u;
+    // walk back while the previous run of the same unit can still reach this one
+    int64_t s = t;
+    while (s > 0) {
+        unsigned long long kp = key[s - 1];
+        if ((int64_t)(kp >> abits) != urev) break;
+        int64_t a_s = (int64_t)(key[s] & amask);
+        int64_t b_p = (int64_t)val[s - 1];
+        if (a_s >= b_p + u) break;
+        s--;
+    }
+    int64_t prev_end = -1, e = 0, cnt = 0;
+    bool emitted = false;
+    for (int64_t r = s; r <= t; r++) {
+        int64_t a = (int64_t)(key[r] & amask), b = (int64_t)val[r];
+        e = a > prev_end ? a : prev_end;
+        emitted = e <= b - L;
+        if (emitted) {
+            cnt = 1 + (b - e) / u;
+            prev_end = e + cnt * u;
+        }
+    }
+    res.emit[t] = emitted ? 1 : 0;
+    if (!emitted) return;
+    // primitive period of the first unit (MotifUtils.smallest_period_str, bwt.py:1124-1133)
+    int64_t prim = u;
+    for (int64_t p = 1; p <= u / 2; p++) {
+        if (u % p) continue;
+        bool ok = true;
+        for (int64_t j = p; j < u; j++)
+            if (__ldg(text + e + j) != __ldg(text + e + j - p)) { ok = false; break; }
+        if (ok) { prim = p; break; }
+    }
+    int64_t end = e + cnt * u;
+    int32_t *row = res.row + t * BWTK_REC_W;
+    row[0] = (int32_t)e; row[1] = (int32_t)end; row[2] = (int32_t)prim;
+    row[3] = (int32_t)(prim < u ? (end - e) / prim : cnt);
+    row[4] = 0; row[5] = 0; row[6] = (int32_t)u; row[7] = 0;
+}
+
+struct CountEmit {
+    const uint8_t *emit;
+    __device__ uint64_t operator()(int64_t i) const { return emit[i]; }
+};
+struct WriteRows {
+    const int32_t *row;
+    int32_t *out;
+    int64_t cap;
+    __device__ void operator()(int64_t i, uint64_t excl, uint64_t cnt) const
+    {
+        if (!cnt || (int64_t)excl >= cap) return;
+        const int4 *src = reinterpret_cast<const int4 *>(row + i * BWTK_REC_W);
+        int4 *dst = reinterpret_cast<int4 *>(out + excl * BWTK_REC_W);
+        dst[0] = src[0];
+        dst[1] = src[1];
+    }
+};
+
+static int bits_for(int64_t v)
+{
+    int b = 1;
+    while ((1ll << b) <= v) b++;
+    return b;
+}
+
+static int64_t cand_capacity(int64_t n) { return n / 2 + 65536; }
+
+}  // namespace strict
+
+// ===========================================================================
+// Tier 1
+// ===========================================================================
+namespace tier1 {
+
+struct Params {
+    const uint8_t *text;
+    const uint8_t *seen;
+    int64_t n;
+    int m;
+    int mc;
+    int min_len;
+    double min_entropy;
+    const double *plogp;  // [10][10]: plogp[L*10 + c] = (c/L)*log2(c/L)
+};
+
+__device__ __forceinline__ bool acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+// "Would the reference emit a repeat if its scan visited position i in this
+// pass?" (bwt.py:1454-1527, with the pre-pass seen mask).  Returns the array
+// end, or -1.
+__device__ int64_t would_emit(const Params &p, int64_t i)
+{
+    const int m = p.m;
+    const int64_t n = p.n;
+    if (i >= n - m) return -1;
+    if (p.seen[i]) return -1;
+    const uint8_t *t = p.text;
+    for (int q = 0; q < m; q++)
+        if (!acgt(__ldg(t + i + q))) return -1;
+    // run of text[j] == text[j+m] from i; copies = 1 + run/m
+    int64_t lim = n - m;
+    int64_t need = (int64_t)(p.mc - 1) * m;
+    int64_t j = i;
+    while (j < lim && __ldg(t + j) == __ldg(t + j + m)) {
+        j++;
+    }
+    int64_t run = j - i;
+    if (run < need) return -1;
+    int64_t copies = 1 + run / m;
+    if (copies < p.mc) return -1;
+    int64_t length = copies * m;
+    if (length < 10) {
+        // entropy of the motif, symbols accumulated in first-seen order
+        int cnt[4] = {0, 0, 0, 0};
+        int order[4], nd = 0;
+        for (int q = 0; q < m; q++) {
+            uint8_t c = __ldg(t + i + q);
+            int k = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
+            if (cnt[k] == 0) order[nd++] = k;
+            cnt[k]++;
+        }
+        double e = 0.0;
+        for (int q = 0; q < nd; q++) e -= p.plogp[m * 10 + cnt[order[q]]];
+        if (e < p.min_entropy) return -1;
+    }
+    if (length < p.min_len) return -1;
+    return i + length;
+}
+
+struct CountCand {
+    Params p;
+    __device__ uint64_t operator()(int64_t i) const { return would_emit(p, i) >= 0 ? 1ull : 0ull; }
+};
+struct EmitCand {
+    Params p;
+    int32_t *cpos;
+    int32_t *cend;
+    int64_t step;
+    int abits;
+    unsigned long long *ckey;  // (pos % step) << abits | pos
+    uint32_t *cidx;
+    __device__ void operator()(int64_t i, uint64_t excl, uint64_t cnt) const
+    {
+        if (!cnt) return;
+        cpos[excl] = (int32_t)i;
+        cend[excl] = (int32_t)would_emit(p, i);
+        ckey[excl] = ((unsigned long long)(i % step) << abits) | (unsigned long long)i;
+        cidx[excl] = (uint32_t)excl;
+    }
+};
+
+// first index in sorted `key` with key >= want, or K
+__device__ __forceinline__ int64_t lower_bound(const unsigned long long *key, int64_t K, unsigned long long want)
+{
+    int64_t lo = 0, hi = K;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (key[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// candidate visited first when the scan (re)starts at position s: smallest
+// candidate position >= s congruent to s modulo step
+__device__ __forceinline__ int32_t next_cand(const unsigned long long *skey, const uint32_t *sidx, int64_t K,
+                                             int64_t s, int64_t step, int abits, int64_t n, int m)
+{
+    if (s >= n - m) return -1;
+    unsigned long long r = (unsigned long long)(s % step);
+    int64_t at = lower_bound(skey, K, (r << abits) | (unsigned long long)s);
+    if (at >= K) return -1;
+    if ((skey[at] >> abits) != r) return -1;
+    return (int32_t)sidx[at];
+}
+
+__global__ void succ_kernel(const int32_t *__restrict__ cend, const unsigned long long *__restrict__ skey,
+                            const uint32_t *__restrict__ sidx, int64_t K, int64_t step, int abits, int64_t n,
+                            int m, int32_t *__restrict__ succ, int32_t *__restrict__ first)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) *first = next_cand(skey, sidx, K, 0, step, abits, n, m);
+    if (k >= K) return;
+    succ[k] = next_cand(skey, sidx, K, cend[k], step, abits, n, m);
+}
+
+__global__ void double_kernel(const int32_t *__restrict__ jin, int32_t *__restrict__ jout, int64_t K)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    int32_t a = jin[k];
+    jout[k] = a < 0 ? -1 : jin[a];
+}
+
+// anchors every 2^kappa hops along the path from `first`
+__global__ void coarse_walk_kernel(const int32_t *__restrict__ jbig, const int32_t *__restrict__ first,
+                                   int32_t *__restrict__ anchor, unsigned *__restrict__ nanchor)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    int32_t v = *first;
+    unsigned a = 0;
+    while (v >= 0) {
+        anchor[a++] = v;
+        v = jbig[v];
+    }
+    *nanchor = a;
+}
+
+__global__ void fine_walk_kernel(const int32_t *__restrict__ succ, const int32_t *__restrict__ anchor,
+                                 const unsigned *__restrict__ nanchor, int64_t hops, uint8_t *__restrict__ onpath)
+{
+    int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= (int64_t)*nanchor) return;
+    int32_t v = anchor[a];
+    for (int64_t h = 0; h < hops && v >= 0; h++) {
+        onpath[v] = 1;
+        v = succ[v];
+    }
+}
+
+struct CountPath {
+    const uint8_t *onpath;
+    __device__ uint64_t operator()(int64_t k) const { return onpath[k]; }
+};
+struct EmitPath {
+    const int32_t *cpos;
+    const int32_t *cend;
+    int m;
+    int32_t *rec;
+    int64_t rec_base;
+    int64_t cap;
+    uint8_t *seen;
+    __device__ void operator()(int64_t k, uint64_t excl, uint64_t cnt) const
+    {
+        if (!cnt) return;
+        int32_t s = cpos[k], e = cend[k];
+        for (int32_t q = s; q < e; q++) seen[q] = 1;
+        int64_t slot = rec_base + (int64_t)excl;
+        if (slot >= cap) return;
+        int32_t *row = rec + slot * BWTK_REC_W;
+        row[0] = s; row[1] = e; row[2] = m; row[3] = (e - s) / m;
+        row[4] = 0; row[5] = 0; row[6] = 0; row[7] = 0;
+    }
+};
+
+}  // namespace tier1
+
+// ===========================================================================
+// LCP plateaus
+// ===========================================================================
+namespace plateau {
+
+__global__ void max_kernel(const int32_t *__restrict__ lcp, int64_t n, int *__restrict__ out)
+{
+    int v = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int x = lcp[i];
+        v = x > v ? x : v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        int t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, v);
+}
+
+// hi 31 bits: plateau starts, lo 31 bits: plateau members
+struct CountMembers {
+    const int32_t *lcp;
+    int thr;
+    __device__ uint64_t operator()(int64_t r) const
+    {
+        bool in = lcp[r] >= thr;
+        bool start = in && (r == 0 || lcp[r - 1] < thr);
+        return ((uint64_t)start << 31) | (uint64_t)in;
+    }
+};
+struct EmitMembers {
+    const int32_t *sa;
+    int abits;
+    unsigned long long *key;  // (segment id << abits) | text position
+    uint32_t *val;
+    __device__ void operator()(int64_t r, uint64_t excl, uint64_t cnt) const
+    {
+        if (!(cnt & 0x7fffffffull)) return;
+        uint64_t seg = (excl >> 31) + (cnt >> 31);  // starts up to and including r
+        uint64_t slot = excl & 0x7fffffffull;
+        key[slot] = (seg << abits) | (uint64_t)(uint32_t)sa[r];
+        val[slot] = 0;
+    }
+};
+
+// per sorted member: arithmetic progression with difference `period`, validation
+// (>= 80 % of positions equal to the first unit), record row
+__global__ void __launch_bounds__(256)
+    progress_kernel(const uint8_t *__restrict__ text, int64_t n_text, const unsigned long long *__restrict__ key,
+                    int64_t M, int abits, int64_t period, int64_t mc, uint8_t *__restrict__ emit,
+                    int32_t *__restrict__ rows)
+{
+    int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= M) return;
+    const unsigned long long amask = (1ull << abits) - 1ull;
+    unsigned long long ka = key[a];
+    unsigned long long seg = ka >> abits;
+    int64_t start = (int64_t)(ka & amask);
+    int64_t copies = 1;
+    for (int64_t b = a + 1; b < M; b++) {
+        unsigned long long kb = key[b];
+        if ((kb >> abits) != seg) break;
+        if ((int64_t)(kb & amask) != start + copies * period) break;
+        copies++;
+    }
+    bool ok = copies >= mc && (start + period <= n_text);
+    if (ok) {
+        int64_t rep_end = start + copies * period;
+        int64_t mlen = (rep_end <= n_text ? rep_end : n_text) - start;
+        ok = mlen >= 2 * period;
+        if (ok) {
+            int64_t match = 0;
+            for (int64_t t = 0; t < mlen; t++)
+                match += (__ldg(text + start + t) == __ldg(text + start + (t % period)));
+            ok = ((double)match / (double)mlen) >= 0.8;
+        }
+        if (ok) {
+            int32_t *row = rows + a * BWTK_REC_W;
+            row[0] = (int32_t)start; row[1] = (int32_t)rep_end; row[2] = (int32_t)period;
+            row[3] = (int32_t)copies; row[4] = 0; row[5] = 0; row[6] = 0; row[7] = 0;
+        }
+    }
+    emit[a] = ok ? 1 : 0;
+}
+
+}  // namespace plateau
+}  // namespace bwtk
+
 using namespace bwtk;
-#define NOTYET(name) do { set_error(name ": kernel not built yet"); return BWTK_EINTERNAL; } while (0)
-extern "C" int64_t bwtk_tier1_workspace_bytes(int64_t) { return 0; }
-extern "C" int32_t bwtk_tier1_scan(const uint8_t *, int64_t, int32_t, int32_t, int32_t, double, int32_t *, int64_t, int64_t *, uint8_t *, void *, int64_t, void *) { NOTYET("tier1_scan"); }
-extern "C" int64_t bwtk_strict_workspace_bytes(int64_t, int64_t) { return 0; }
-extern "C" int32_t bwtk_strict_scan(const uint8_t *, int64_t, int64_t, int64_t, int64_t, int64_t, int32_t *, int64_t, int64_t *, void *, int64_t, void *) { NOTYET("strict_scan"); }
-extern "C" int64_t bwtk_plateau_workspace_bytes(int64_t) { return 0; }
-extern "C" int32_t bwtk_lcp_plateaus(const uint8_t *, int64_t, const int32_t *, const int32_t *, int64_t, int64_t, int64_t, int64_t, int32_t *, int64_t, int64_t *, int64_t *, void *, int64_t, void *) { NOTYET("lcp_plateaus"); }
+
+// ---------------------------------------------------------------------------
+// strict scan entry point
+// ---------------------------------------------------------------------------
+extern "C" int64_t bwtk_strict_workspace_bytes(int64_t n, int64_t)
+{
+    if (n < 1) n = 1;
+    int64_t cap = strict::cand_capacity(n);
+    return 2 * align_up(cap * 8, 256) + 2 * align_up(cap * 4, 256) + align_up(cap, 256) +
+           align_up(cap * BWTK_REC_W * 4, 256) + rsort::workspace_bytes(cap) + scan::workspace_bytes(cap) +
+           8192;
+}
+
+extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int64_t min_unit_len,
+                                    int64_t max_unit_len, int64_t max_mismatch, int64_t min_copies,
+                                    int32_t *d_rec, int64_t cap, int64_t *h_count, void *d_ws,
+                                    int64_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    BWTK_REQUIRE(h_count, "null count");
+    *h_count = 0;
+    BWTK_REQUIRE(min_copies >= 2, "min_copies must be >= 2");
+    BWTK_REQUIRE(min_unit_len >= 1, "min_unit_len must be >= 1");
+    BWTK_REQUIRE(max_mismatch == 0, "device strict scan implements max_mismatch == 0 (the CLI's setting)");
+    if (n_total <= 0) return BWTK_OK;
+    BWTK_REQUIRE(d_text && d_ws && (d_rec || cap == 0), "null pointer");
+    BWTK_REQUIRE(n_total < (1ll << 30), "n must be < 2^30");
+    int64_t n = n_total;
+    {   // exclude a trailing '$' (bwt.py:1915-1916)
+        uint8_t last = 0;
+        BWTK_CUDA(cudaMemcpyAsync(&last, d_text + n - 1, 1, cudaMemcpyDeviceToHost, st));
+        BWTK_CUDA(cudaStreamSynchronize(st));
+        if (last == 36) n--;
+    }
+    int64_t umax = n / min_copies < max_unit_len ? n / min_copies : max_unit_len;
+    if (umax < min_unit_len || n <= 0) return BWTK_OK;
+    BWTK_REQUIRE(umax <= 60000, "max_unit_len above 60000 is not supported on device");
+    if (ws_bytes < bwtk_strict_workspace_bytes(n_total, max_unit_len)) {
+        set_error("strict workspace: need %lld bytes", (long long)bwtk_strict_workspace_bytes(n_total, max_unit_len));
+        return BWTK_EWORKSPACE;
+    }
+    const int64_t ccap = strict::cand_capacity(n_total);
+    Carver c(d_ws, ws_bytes);
+    unsigned long long *key0 = c.take<unsigned long long>(ccap);
+    unsigned long long *key1 = c.take<unsigned long long>(ccap);
+    uint32_t *val0 = c.take<uint32_t>(ccap);
+    uint32_t *val1 = c.take<uint32_t>(ccap);
+    uint8_t *emit = c.take<uint8_t>(ccap);
+    int32_t *rows = c.take<int32_t>(ccap * BWTK_REC_W);
+    rsort::Workspace rws = rsort::carve(c, ccap);
+    scan::Workspace sws = scan::carve(c, ccap);
+    unsigned long long *d_count = c.take<unsigned long long>(2);
+    if (!c.ok()) { set_error("strict workspace carve overflow"); return BWTK_EWORKSPACE; }
+    BWTK_CUDA(cudaMemsetAsync(d_count, 0, 16, st));
+    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
+    BWTK_CUDA(cudaMemsetAsync(sws.err, 0, sizeof(int), st));
+
+    strict::CandOut out;
+    out.key = key0; out.val = val0; out.count = d_count; out.cap = ccap;
+    out.abits = strict::bits_for(n); out.umax = umax;
+
+    // units with (mc-1)*u < 8 take the per-position kernel, the rest the ballot kernel
+    int64_t small_hi = 7 / (min_copies - 1);
+    if (small_hi > umax) small_hi = umax;
+    if (small_hi >= min_unit_len) {
+        strict::find_runs_small_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_text, n, min_unit_len,
+                                                                                  small_hi, min_copies, out);
+        BWTK_LAUNCH_CHECK();
+    }
+    int64_t big_lo = small_hi + 1 > min_unit_len ? small_hi + 1 : min_unit_len;
+    if (big_lo <= umax) {
+        int64_t tiles = ceil_div(n, strict::TP);
+        int64_t nu = umax - big_lo + 1;
+        // enough CTAs to fill the machine even for short contigs
+        int64_t ysplit = ceil_div((int64_t)NUM_SMS * 8, tiles);
+        if (ysplit > nu) ysplit = nu;
+        if (ysplit < 1) ysplit = 1;
+        if (ysplit > 65535) ysplit = 65535;
+        int64_t u_per_block = ceil_div(nu, ysplit);
+        ysplit = ceil_div(nu, u_per_block);
+        size_t smem = (size_t)(strict::TP + umax + 16);
+        static size_t smem_set = 0;
+        if (smem > 48 * 1024 && smem > smem_set) {
+            BWTK_CUDA(cudaFuncSetAttribute(strict::find_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+            smem_set = smem;
+        }
+        dim3 grid((unsigned)tiles, (unsigned)ysplit);
+        strict::find_runs_kernel<<<grid, strict::THREADS, smem, st>>>(d_text, n, big_lo, umax, u_per_block,
+                                                                      min_copies, out);
+        BWTK_LAUNCH_CHECK();
+    }
+    unsigned long long h_cand = 0;
+    BWTK_CUDA(cudaMemcpyAsync(&h_cand, d_count, 8, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    if ((int64_t)h_cand > ccap) {
+        set_error("strict scan: %llu candidate runs exceed the workspace capacity %lld", h_cand, (long long)ccap);
+        return BWTK_EWORKSPACE;
+    }
+    int64_t m = (int64_t)h_cand;
+    if (m == 0) return BWTK_OK;
+    int in_first = 1;
+    int rc = rsort::sort_pairs<unsigned long long>(key0, val0, key1, val1, m, 0,
+                                                   out.abits + strict::bits_for(umax), rws, st, &in_first,
+                                                   nullptr);
+    if (rc) return rc;
+    const unsigned long long *sk = in_first ? key0 : key1;
+    const uint32_t *sv = in_first ? val0 : val1;
+    strict::Resolved res{emit, rows};
+    strict::resolve_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(d_text, sk, sv, m, out.abits, umax,
+                                                                      min_copies, res);
+    BWTK_LAUNCH_CHECK();
+    strict::CountEmit ce{emit};
+    strict::WriteRows wr{rows, d_rec, cap};
+    rc = scan::run(m, ce, wr, sws, st);
+    if (rc) return rc;
+    unsigned long long h_total = 0;
+    int h_err[2] = {0, 0};
+    BWTK_CUDA(cudaMemcpyAsync(&h_total, sws.total, 8, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaMemcpyAsync(&h_err[0], rws.err, 4, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaMemcpyAsync(&h_err[1], sws.err, 4, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    if (h_err[0] || h_err[1]) { set_error("look-back spin limit hit in strict scan"); return BWTK_EINTERNAL; }
+    *h_count = (int64_t)h_total;
+    if ((int64_t)h_total > cap) {
+        set_error("strict scan: %llu records exceed capacity %lld", h_total, (long long)cap);
+        return BWTK_EOVERFLOW;
+    }
+    return BWTK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Tier 1 entry point
+// ---------------------------------------------------------------------------
+extern "C" int64_t bwtk_tier1_workspace_bytes(int64_t n)
+{
+    if (n < 1) n = 1;
+    // seen + (cpos,cend,cidx,cidx2,succ,j0,j1,anchor) + (ckey x2) + onpath + sort/scan scratch + entropy table
+    return align_up(n, 256) + 8 * align_up(n * 4, 256) + 2 * align_up(n * 8, 256) + align_up(n, 256) +
+           rsort::workspace_bytes(n) + scan::workspace_bytes(n) + 8192;
+}
+
+extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max_motif_len,
+                                   int32_t min_copies, int32_t min_array_len, double min_entropy,
+                                   int32_t *d_rec, int64_t cap, int64_t *h_count, uint8_t *d_seen_out,
+                                   void *d_ws, int64_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    BWTK_REQUIRE(h_count, "null count");
+    *h_count = 0;
+    if (n <= 0) return BWTK_OK;
+    BWTK_REQUIRE(d_text && d_ws && (d_rec || cap == 0), "null pointer");
+    BWTK_REQUIRE(n < (1ll << 30), "n must be < 2^30");
+    BWTK_REQUIRE(min_copies >= 1, "min_copies must be >= 1");
+    if (ws_bytes < bwtk_tier1_workspace_bytes(n)) {
+        set_error("tier1 workspace: need %lld bytes", (long long)bwtk_tier1_workspace_bytes(n));
+        return BWTK_EWORKSPACE;
+    }
+    Carver c(d_ws, ws_bytes);
+    uint8_t *seen = c.take<uint8_t>(n);
+    int32_t *cpos = c.take<int32_t>(n);
+    int32_t *cend = c.take<int32_t>(n);
+    uint32_t *cidx0 = c.take<uint32_t>(n);
+    uint32_t *cidx1 = c.take<uint32_t>(n);
+    int32_t *succ = c.take<int32_t>(n);
+    int32_t *j0 = c.take<int32_t>(n);
+    int32_t *j1 = c.take<int32_t>(n);
+    int32_t *anchor = c.take<int32_t>(n);
+    unsigned long long *ckey0 = c.take<unsigned long long>(n);
+    unsigned long long *ckey1 = c.take<unsigned long long>(n);
+    uint8_t *onpath = c.take<uint8_t>(n);
+    rsort::Workspace rws = rsort::carve(c, n);
+    scan::Workspace sws = scan::carve(c, n);
+    double *d_plogp = c.take<double>(100);
+    int32_t *d_first = c.take<int32_t>(4);
+    unsigned *d_nanchor = c.take<unsigned>(4);
+    if (!c.ok()) { set_error("tier1 workspace carve overflow"); return BWTK_EWORKSPACE; }
+    BWTK_CUDA(cudaMemsetAsync(seen, 0, (size_t)n, st));
+    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
+    BWTK_CUDA(cudaMemsetAsync(sws.err, 0, sizeof(int), st));
+    // (c/L)*log2(c/L) in IEEE double, the same expression the host evaluates
+    double plogp[100];
+    for (int L = 0; L < 10; L++)
+        for (int k = 0; k < 10; k++) {
+            double v = 0.0;
+            if (L > 0 && k > 0 && k <= L) { double p = (double)k / (double)L; v = p * log2(p); }
+            plogp[L * 10 + k] = v;
+        }
+    BWTK_CUDA(cudaMemcpyAsync(d_plogp, plogp, sizeof(plogp), cudaMemcpyHostToDevice, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+
+    int64_t step = n > 10000000 ? 50 : (n > 5000000 ? 20 : 1);
+    const int abits = strict::bits_for(n);
+    const int sbits = strict::bits_for(step);
+    int64_t total = 0;
+    int mmax = max_motif_len < 9 ? max_motif_len : 9;
+    for (int m = mmax; m >= 1; m--) {
+        if (n - m <= 0) continue;
+        tier1::Params p{d_text, seen, n, m, min_copies, min_array_len, min_entropy, d_plogp};
+        tier1::CountCand cc{p};
+        tier1::EmitCand ec{p, cpos, cend, step, abits, ckey0, cidx0};
+        int rc = scan::run(n - m, cc, ec, sws, st);
+        if (rc) return rc;
+        unsigned long long hK = 0;
+        BWTK_CUDA(cudaMemcpyAsync(&hK, sws.total, 8, cudaMemcpyDeviceToHost, st));
+        BWTK_CUDA(cudaStreamSynchronize(st));
+        int64_t K = (int64_t)hK;
+        if (K == 0) continue;
+        const unsigned long long *skey = ckey0;
+        const uint32_t *sidx = cidx0;
+        if (step > 1) {
+            int in_first = 1;
+            rc = rsort::sort_pairs<unsigned long long>(ckey0, cidx0, ckey1, cidx1, K, 0, abits + sbits, rws, st,
+                                                       &in_first, nullptr);
+            if (rc) return rc;
+            skey = in_first ? ckey0 : ckey1;
+            sidx = in_first ? cidx0 : cidx1;
+        }
+        tier1::succ_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(cend, skey, sidx, K, step, abits, n, m,
+                                                                     succ, d_first);
+        BWTK_LAUNCH_CHECK();
+        // jump table for 2^kappa hops, kappa ~ log2(K)/2
+        int kappa = 0;
+        while ((1ll << (2 * kappa)) < K) kappa++;
+        const int32_t *jbig = succ;
+        int32_t *ja = j0, *jb = j1;
+        for (int r = 0; r < kappa; r++) {
+            tier1::double_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(jbig, ja, K);
+            BWTK_LAUNCH_CHECK();
+            jbig = ja;
+            int32_t *t = ja; ja = jb; jb = t;
+        }
+        tier1::coarse_walk_kernel<<<1, 32, 0, st>>>(jbig, d_first, anchor, d_nanchor);
+        BWTK_LAUNCH_CHECK();
+        BWTK_CUDA(cudaMemsetAsync(onpath, 0, (size_t)K, st));
+        // at most ceil(K / 2^kappa) + 1 anchors
+        int64_t max_anchor = (K >> kappa) + 2;
+        tier1::fine_walk_kernel<<<(unsigned)ceil_div(max_anchor, 128), 128, 0, st>>>(succ, anchor, d_nanchor,
+                                                                                   1ll << kappa, onpath);
+        BWTK_LAUNCH_CHECK();
+        tier1::CountPath cp{onpath};
+        tier1::EmitPath ep{cpos, cend, m, d_rec, total, cap, seen};
+        rc = scan::run(K, cp, ep, sws, st);
+        if (rc) return rc;
+        unsigned long long hE = 0;
+        BWTK_CUDA(cudaMemcpyAsync(&hE, sws.total, 8, cudaMemcpyDeviceToHost, st));
+        BWTK_CUDA(cudaStreamSynchronize(st));
+        total += (int64_t)hE;
+    }
+    int h_err[2] = {0, 0};
+    BWTK_CUDA(cudaMemcpyAsync(&h_err[0], rws.err, 4, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaMemcpyAsync(&h_err[1], sws.err, 4, cudaMemcpyDeviceToHost, st));
+    if (d_seen_out) BWTK_CUDA(cudaMemcpyAsync(d_seen_out, seen, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    if (h_err[0] || h_err[1]) { set_error("look-back spin limit hit in tier1 scan"); return BWTK_EINTERNAL; }
+    *h_count = total;
+    if (total > cap) {
+        set_error("tier1 scan: %lld records exceed capacity %lld", (long long)total, (long long)cap);
+        return BWTK_EOVERFLOW;
+    }
+    return BWTK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// LCP plateau entry point
+// ---------------------------------------------------------------------------
+extern "C" int64_t bwtk_plateau_workspace_bytes(int64_t n)
+{
+    if (n < 1) n = 1;
+    return 2 * align_up(n * 8, 256) + 2 * align_up(n * 4, 256) + align_up(n, 256) +
+           align_up(n * BWTK_REC_W * 4, 256) + rsort::workspace_bytes(n) + scan::workspace_bytes(n) + 8192;
+}
+
+extern "C" int32_t bwtk_lcp_plateaus(const uint8_t *d_text, int64_t n_text, const int32_t *d_sa,
+                                     const int32_t *d_lcp, int64_t n, int64_t min_period, int64_t max_period,
+                                     int64_t min_copies, int32_t *d_rec, int64_t cap, int64_t *h_count,
+                                     int64_t *h_threshold, void *d_ws, int64_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    BWTK_REQUIRE(h_count && h_threshold, "null output");
+    *h_count = 0;
+    *h_threshold = -1;
+    if (n <= 0) return BWTK_OK;
+    BWTK_REQUIRE(d_text && d_sa && d_lcp && d_ws && (d_rec || cap == 0), "null pointer");
+    BWTK_REQUIRE(n < (1ll << 30) && n_text < (1ll << 30), "n must be < 2^30");
+    if (ws_bytes < bwtk_plateau_workspace_bytes(n)) {
+        set_error("plateau workspace: need %lld bytes", (long long)bwtk_plateau_workspace_bytes(n));
+        return BWTK_EWORKSPACE;
+    }
+    Carver c(d_ws, ws_bytes);
+    unsigned long long *key0 = c.take<unsigned long long>(n);
+    unsigned long long *key1 = c.take<unsigned long long>(n);
+    uint32_t *val0 = c.take<uint32_t>(n);
+    uint32_t *val1 = c.take<uint32_t>(n);
+    uint8_t *emit = c.take<uint8_t>(n);
+    int32_t *rows = c.take<int32_t>(n * BWTK_REC_W);
+    rsort::Workspace rws = rsort::carve(c, n);
+    scan::Workspace sws = scan::carve(c, n);
+    int *d_max = c.take<int>(4);
+    if (!c.ok()) { set_error("plateau workspace carve overflow"); return BWTK_EWORKSPACE; }
+    BWTK_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
+    BWTK_CUDA(cudaMemsetAsync(sws.err, 0, sizeof(int), st));
+    int grid = (int)(ceil_div(n, 256 * 8) < NUM_SMS * 8 ? ceil_div(n, 256 * 8) : NUM_SMS * 8);
+    plateau::max_kernel<<<grid, 256, 0, st>>>(d_lcp, n, d_max);
+    BWTK_LAUNCH_CHECK();
+    int h_max = 0;
+    BWTK_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    // threshold (bwt.py:2124-2129)
+    if (h_max < min_period) return BWTK_OK;
+    int64_t thr = max_period < h_max ? max_period : h_max;
+    if (thr > 20) thr = 20;
+    if (thr < min_period) thr = min_period;
+    *h_threshold = thr;
+    if (thr <= 0) {
+        set_error("plateau threshold %lld is not positive", (long long)thr);
+        return BWTK_EINVAL;
+    }
+    const int abits = strict::bits_for(n_text > n ? n_text : n);
+    plateau::CountMembers cm{d_lcp, (int)thr};
+    plateau::EmitMembers em{d_sa, abits, key0, val0};
+    int rc = scan::run(n, cm, em, sws, st);
+    if (rc) return rc;
+    unsigned long long h_tot = 0;
+    BWTK_CUDA(cudaMemcpyAsync(&h_tot, sws.total, 8, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    int64_t M = (int64_t)(h_tot & 0x7fffffffull);
+    int64_t segs = (int64_t)(h_tot >> 31);
+    if (M == 0) return BWTK_OK;
+    int in_first = 1;
+    rc = rsort::sort_pairs<unsigned long long>(key0, val0, key1, val1, M, 0, abits + strict::bits_for(segs), rws,
+                                               st, &in_first, nullptr);
+    if (rc) return rc;
+    const unsigned long long *sk = in_first ? key0 : key1;
+    plateau::progress_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(d_text, n_text, sk, M, abits, thr,
+                                                                        min_copies, emit, rows);
+    BWTK_LAUNCH_CHECK();
+    strict::CountEmit ce{emit};
+    strict::WriteRows wr{rows, d_rec, cap};
+    rc = scan::run(M, ce, wr, sws, st);
+    if (rc) return rc;
+    unsigned long long h_total = 0;
+    int h_err[2] = {0, 0};
+    BWTK_CUDA(cudaMemcpyAsync(&h_total, sws.total, 8, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaMemcpyAsync(&h_err[0], rws.err, 4, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaMemcpyAsync(&h_err[1], sws.err, 4, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    if (h_err[0] || h_err[1]) { set_error("look-back spin limit hit in plateau scan"); return BWTK_EINTERNAL; }
+    *h_count = (int64_t)h_total;
+    if ((int64_t)h_total > cap) {
+        set_error("plateau scan: %llu records exceed capacity %lld", h_total, (long long)cap);
+        return BWTK_EOVERFLOW;
+    }
+    return BWTK_OK;
+}
