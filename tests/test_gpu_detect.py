@@ -86,3 +86,62 @@ def test_tier1_sampling_regimes(detect, oracle):
     got = detect.tier1_rows(s)
     assert np.array_equal(got, want)
     assert len(got) > 100
+
+
+def _ext_texts():
+    s = gen_contig(8000, 17, sub_rate=0.06)
+    s[2500:2600] = ord("N")
+    return [("planted_8000", s.tobytes() + b"$"),
+            ("imperfect_runs", (b"ACGTAC" * 20 + b"ACGAAC" + b"ACGTAC" * 9 + b"TTTTTTTTTT" + b"CAG" * 30 + b"CAA" + b"CAG" * 8) * 3 + b"$"),
+            ("AC_period2", b"AC" * 700 + b"A$")]
+
+
+@pytest.mark.parametrize("name,text", _ext_texts())
+def test_extend_and_consensus_batches(detect, oracle, name, text):
+    rng = np.random.default_rng(len(text))
+    n_total = len(text)
+    n = n_total - 1
+    seeds, periods, flags = [], [], []
+    for _ in range(600):
+        p = int(rng.integers(1, 40))
+        if n < 3 * p:
+            continue
+        seeds.append(int(rng.integers(0, n - 2 * p)))
+        periods.append(p)
+        flags.append(int(rng.integers(0, 2)))
+    got = detect.extend_batch(text, n, seeds, periods, flags, mode=0)
+    for i, (s0, p, f) in enumerate(zip(seeds, periods, flags)):
+        want = oracle.extend_with_mismatches(text, s0, p, n, bool(f))
+        assert tuple(int(x) for x in got[i, :5]) == want, (name, s0, p, f)
+    got = detect.extend_batch(text, n_total, seeds, periods, None, mode=1)
+    for i, (s0, p) in enumerate(zip(seeds, periods)):
+        want = oracle.extend_tandem_fm(text, s0, p)
+        assert tuple(int(x) for x in got[i, :3]) == want, (name, s0, p)
+    copies = [int(x) for x in rng.integers(1, 12, len(seeds))]
+    cons, mm = detect.consensus_batch(text, seeds, periods, copies)
+    for i, (s0, p, c) in enumerate(zip(seeds, periods, copies)):
+        wc, wrate, wmax = oracle.consensus(text, s0, p, c)
+        assert np.array_equal(cons[i][: wc.size], wc) and (wc.size == 0 or cons[i].size == wc.size)
+        used = int(mm[i, 2])
+        rate = (mm[i, 0] / (used * p)) if used else 0.0
+        assert rate == wrate and int(mm[i, 1]) == wmax
+
+
+@pytest.mark.parametrize("n,seed", [(600, 3), (1200, 4), (3000, 1), (9000, 12), (20_000, 5), (120_000, 9)])
+def test_period_scan_rows(detect, oracle, n, seed):
+    s = gen_contig(n, seed, sub_rate=0.04)
+    if n >= 9000:
+        s[n // 2: n // 2 + 300] = ord("N")
+    text = s.tobytes() + b"$"
+    want, wit = oracle.period_scan(text)
+    got, git = detect.period_scan_rows(text)
+    assert git == wit
+    assert np.array_equal(got, want), f"n={n}: {len(got)} vs {len(want)} rows"
+    # with a Tier 1 mask and without mismatches
+    t1 = oracle.tier1_scan(text)
+    mask = np.zeros(len(text) - 1, np.uint8)
+    for r in t1:
+        mask[r[0]:min(r[1], mask.size)] = 1
+    want, wit = oracle.period_scan(text, allow_mismatches=False, tier1_mask=mask, min_period=2, max_period=60)
+    got, git = detect.period_scan_rows(text, allow_mismatches=False, tier1_mask=mask, min_period=2, max_period=60)
+    assert git == wit and np.array_equal(got, want)
