@@ -41,6 +41,26 @@ void count_launch(int k = 1);
         }                                                                            \
     } while (0)
 
+// Optional per-kernel timing (bwtk_profile_enable): CUDA events recorded on the
+// launching stream around a named launch, with its algorithmic byte count.
+namespace prof {
+bool enabled();
+void begin(const char *name, int64_t algo_bytes, cudaStream_t st);
+void end(cudaStream_t st);
+struct Scope {
+    cudaStream_t st;
+    bool on;
+    Scope(const char *name, int64_t algo_bytes, cudaStream_t s) : st(s), on(enabled())
+    {
+        if (on) begin(name, algo_bytes, st);
+    }
+    ~Scope()
+    {
+        if (on) end(st);
+    }
+};
+}  // namespace prof
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -3,6 +3,10 @@
 
 #include <stdarg.h>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 namespace bwtk {
 
@@ -17,6 +21,34 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 void count_launch(int k) { g_launches += k; }
+
+namespace prof {
+struct Rec {
+    const char *name;
+    int64_t bytes;
+    cudaEvent_t e0, e1;
+};
+static bool g_on = false;
+static std::vector<Rec> g_recs;
+static std::mutex g_mu;
+bool enabled() { return g_on; }
+void begin(const char *name, int64_t algo_bytes, cudaStream_t st)
+{
+    Rec r;
+    r.name = name;
+    r.bytes = algo_bytes;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    std::lock_guard<std::mutex> g(g_mu);
+    g_recs.push_back(r);
+}
+void end(cudaStream_t st)
+{
+    std::lock_guard<std::mutex> g(g_mu);
+    if (!g_recs.empty()) cudaEventRecord(g_recs.back().e1, st);
+}
+}  // namespace prof
 
 // ------------------------------------------------------------------ histogram
 __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restrict__ text, int64_t n,
@@ -67,7 +99,8 @@ int byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, unsigned
     if (n > 0) {
         int64_t want = ceil_div(n, 256 * 64);
         int grid = (int)(want < 1 ? 1 : (want > NUM_SMS * 8 ? NUM_SMS * 8 : want));
-        byte_hist_kernel<<<grid, 256, 0, st>>>(d_text, n, d_scratch);
+        { prof::Scope ps("byte_hist_kernel", n, st);
+        byte_hist_kernel<<<grid, 256, 0, st>>>(d_text, n, d_scratch); }
         BWTK_LAUNCH_CHECK();
     }
     BWTK_CUDA(cudaMemcpyAsync(h_totals, d_scratch, 256 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -112,8 +145,9 @@ int pack_text(const uint8_t *d_text, int64_t n, const uint8_t *h_lut, int bits, 
 {
     BWTK_CUDA(cudaMemcpyAsync(d_lut_scratch, h_lut, 256, cudaMemcpyHostToDevice, st));
     int64_t nwords = packed_words(n, bits);
+    { prof::Scope ps("pack_kernel", n + nwords * 4, st);
     pack_kernel<<<(unsigned)ceil_div(nwords, 256), 256, 0, st>>>(d_text, n, d_lut_scratch, bits,
-                                                                 d_packed, nwords);
+                                                                 d_packed, nwords); }
     BWTK_LAUNCH_CHECK();
     // the LUT came from the caller's stack: make sure the copy has been consumed
     BWTK_CUDA(cudaStreamSynchronize(st));
@@ -288,6 +322,46 @@ extern "C" int32_t bwtk_last_error(char *buf, int32_t buflen)
 
 extern "C" int64_t bwtk_launch_count(void) { return (int64_t)g_launches.load(); }
 
+extern "C" int32_t bwtk_profile_enable(int32_t on)
+{
+    prof::g_on = on != 0;
+    return BWTK_OK;
+}
+
+// Synchronises the device, aggregates the recorded launches by name and writes
+// "name\tlaunches\ttotal_ms\talgorithmic_bytes\n" lines; clears the records.
+extern "C" int32_t bwtk_profile_report(char *buf, int32_t buflen)
+{
+    if (!buf || buflen <= 0) return BWTK_EINVAL;
+    cudaDeviceSynchronize();
+    struct Agg { int64_t n = 0; double ms = 0; int64_t bytes = 0; };
+    std::map<std::string, Agg> agg;
+    std::vector<std::string> order;
+    {
+        std::lock_guard<std::mutex> g(prof::g_mu);
+        for (auto &r : prof::g_recs) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.e0, r.e1);
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+            if (!agg.count(r.name)) order.push_back(r.name);
+            Agg &a = agg[r.name];
+            a.n++; a.ms += ms; a.bytes += r.bytes;
+        }
+        prof::g_recs.clear();
+    }
+    std::string out;
+    char line[256];
+    for (auto &nm : order) {
+        Agg &a = agg[nm];
+        snprintf(line, sizeof(line), "%s\t%lld\t%.6f\t%lld\n", nm.c_str(), (long long)a.n, a.ms, (long long)a.bytes);
+        out += line;
+    }
+    strncpy(buf, out.c_str(), (size_t)buflen - 1);
+    buf[buflen - 1] = 0;
+    return BWTK_OK;
+}
+
 extern "C" int32_t bwtk_byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, void *stream)
 {
     BWTK_REQUIRE(h_totals && n >= 0, "bad arguments");
@@ -317,10 +391,12 @@ extern "C" int32_t bwtk_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int6
     int64_t warps_needed = nblk;
     int64_t grid = ceil_div(warps_needed, 8);
     if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
+    { prof::Scope ps("bwt_block_kernel", n * 5 + (int64_t)nrows * ncp * 4, st);
     bwt_block_kernel<<<(unsigned)grid, 256, 0, st>>>(d_text, d_sa, n, occ_rate, d_rows, nrows, d_bwt,
-                                                     d_occ, ncp, nblk);
+                                                     d_occ, ncp, nblk); }
     BWTK_LAUNCH_CHECK();
-    occ_scan_kernel<<<nrows, 1024, 0, st>>>(d_occ, ncp, nblk);
+    { prof::Scope ps("occ_scan_kernel", (int64_t)nrows * ncp * 8, st);
+    occ_scan_kernel<<<nrows, 1024, 0, st>>>(d_occ, ncp, nblk); }
     BWTK_LAUNCH_CHECK();
     BWTK_CUDA(cudaStreamSynchronize(st));  // h_row_of_code is caller memory
     return BWTK_OK;
@@ -355,7 +431,8 @@ extern "C" int32_t bwtk_lcp_build(const uint8_t *d_text, const int32_t *d_sa, in
     if (bits < 0) { set_error("choose_packing failed"); return BWTK_ECUDA; }
     rc = pack_text(d_text, n, lut, bits, packed, d_lut, st);
     if (rc) return rc;
-    lcp_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(packed, d_sa, n, bits, fast ? 1 : 0, d_lcp);
+    { prof::Scope ps("lcp_kernel", n * 8, st);
+    lcp_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(packed, d_sa, n, bits, fast ? 1 : 0, d_lcp); }
     BWTK_LAUNCH_CHECK();
     return BWTK_OK;
 }

@@ -289,7 +289,8 @@ int sort_pairs(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, int64_t n, int bi
     BWTK_CUDA(cudaMemsetAsync(ws.ghist, 0, MAX_PASSES * RADIX * 4, st));
     BWTK_CUDA(cudaMemsetAsync(ws.counters, 0, MAX_PASSES * sizeof(unsigned), st));
     int hgrid = (int)(ceil_div(n, 512 * 16) < NUM_SMS * 4 ? ceil_div(n, 512 * 16) : NUM_SMS * 4);
-    hist_kernel<KeyT><<<hgrid, 512, 0, st>>>(k0, n, plan, ws.ghist);
+    { prof::Scope ps(sizeof(KeyT) == 4 ? "radix_hist_u32" : "radix_hist_u64", n * (int64_t)sizeof(KeyT), st);
+    hist_kernel<KeyT><<<hgrid, 512, 0, st>>>(k0, n, plan, ws.ghist); }
     BWTK_LAUNCH_CHECK();
     scan_hist_kernel<<<plan.passes, RADIX, 0, st>>>(ws.ghist);
     BWTK_LAUNCH_CHECK();
@@ -297,9 +298,10 @@ int sort_pairs(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, int64_t n, int bi
     uint32_t *vin = v0, *vout = v1;
     for (int p = 0; p < plan.passes; p++) {
         BWTK_CUDA(cudaMemsetAsync(ws.status, 0, (size_t)tiles * RADIX * 4, st));
+        { prof::Scope ps(sizeof(KeyT) == 4 ? "onesweep_u32" : "onesweep_u64", 2 * n * (int64_t)(sizeof(KeyT) + 4), st);
         onesweep_kernel<KeyT><<<(unsigned)tiles, THREADS, onesweep_smem<KeyT>(), st>>>(
             kin, vin, kout, vout, n, plan.shift[p], (1u << plan.bits[p]) - 1u,
-            ws.ghist + p * RADIX, ws.status, ws.counters + p, ws.err);
+            ws.ghist + p * RADIX, ws.status, ws.counters + p, ws.err); }
         BWTK_LAUNCH_CHECK();
         KeyT *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;

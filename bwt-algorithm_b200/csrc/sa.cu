@@ -281,7 +281,8 @@ extern "C" int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa
     }
     {
         int thr = 256;
-        sa::init_keys_kernel<<<(unsigned)ceil_div(n, thr), thr, 0, st>>>(packed, n, bits, S, key32a, val0);
+        { prof::Scope ps("init_keys_kernel", n * 8 + n * bits / 8, st);
+        sa::init_keys_kernel<<<(unsigned)ceil_div(n, thr), thr, 0, st>>>(packed, n, bits, S, key32a, val0); }
         BWTK_LAUNCH_CHECK();
         rc = rsort::sort_pairs<uint32_t>(key32a, val0, key32b, val1, n, 0, S * bits, rws, st, &in_first,
                                          &passes);
@@ -297,9 +298,10 @@ extern "C" int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa
         int64_t tiles = ceil_div(n, sa::RG_TILE);
         BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
         BWTK_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), st));
+        { prof::Scope ps("regroup_first", n * 16, st);
         sa::regroup_kernel<uint32_t, true><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
             skey32, sval, nullptr, n, n - S + 1, d_sa, rank, pos_out, suf_other, grp, rg_status,
-            counters, counters + 1, rws.err);
+            counters, counters + 1, rws.err); }
         BWTK_LAUNCH_CHECK();
         BWTK_CUDA(cudaMemcpyAsync(&h_count, counters + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         BWTK_CUDA(cudaStreamSynchronize(st));
@@ -317,8 +319,9 @@ extern "C" int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa
         int64_t m = h_count;
         sum_active += m;
         rounds++;
+        { prof::Scope ps("build_keys_kernel", m * 20, st);
         sa::build_keys_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(suf_in, grp, rank, m, n, h,
-                                                                         kbits, keyA);
+                                                                         kbits, keyA); }
         BWTK_LAUNCH_CHECK();
         rc = rsort::sort_pairs<uint64_t>(keyA, suf_in, keyB, suf_free, m, 0, kbits + gbits, rws, st,
                                          &in_first, &passes);
@@ -329,9 +332,10 @@ extern "C" int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa
         int64_t tiles = ceil_div(m, sa::RG_TILE);
         BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
         BWTK_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), st));
+        { prof::Scope ps("regroup_round", m * 36, st);
         sa::regroup_kernel<uint64_t, false><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
             sk, ss, pos_in, m, 0, d_sa, rank, pos_out, sn, grp, rg_status, counters, counters + 1,
-            rws.err);
+            rws.err); }
         BWTK_LAUNCH_CHECK();
         BWTK_CUDA(cudaMemcpyAsync(&h_count, counters + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         BWTK_CUDA(cudaStreamSynchronize(st));

@@ -45,6 +45,14 @@ int32_t bwtk_last_error(char *buf, int32_t buflen);
 /* number of kernels this library has launched in the calling process */
 int64_t bwtk_launch_count(void);
 
+/* Optional per-kernel timing for bench.py: when enabled, CUDA events are
+ * recorded on the launching stream around the main kernels.
+ * bwtk_profile_report synchronises the device, writes one
+ * "name\tlaunches\ttotal_ms\talgorithmic_bytes\n" line per kernel into buf and
+ * clears the records.  (No counterpart in the reference.) */
+int32_t bwtk_profile_enable(int32_t on);
+int32_t bwtk_profile_report(char *buf, int32_t buflen);
+
 /* ---- a5: BWTCore._build_char_counts (bwt.py:276-286) ------------------
  * byte histogram of the text; h_totals[256] (host) receives the counts.
  * The exclusive prefix sum over present bytes (the FM "C" array) is a 256-entry
