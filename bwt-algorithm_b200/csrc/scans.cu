@@ -284,12 +284,21 @@ __device__ int64_t would_emit(const Params &p, int64_t i)
     return i + length;
 }
 
-struct CountCand {
+// Tier 1 candidate functor: end of the array the reference would emit at i, or -1
+struct Tier1Cand {
     Params p;
-    __device__ uint64_t operator()(int64_t i) const { return would_emit(p, i) >= 0 ? 1ull : 0ull; }
+    __device__ int64_t operator()(int64_t i) const { return would_emit(p, i); }
 };
-struct EmitCand {
-    Params p;
+
+// ---- generic greedy replay ---------------------------------------------------
+// Cand: __device__ int64_t operator()(int64_t i)  -> array end if the reference's
+//       scan would emit when it visits i (a pure function of the pre-pass state), else -1
+template <typename Cand> struct CountCand {
+    Cand c;
+    __device__ uint64_t operator()(int64_t i) const { return c(i) >= 0 ? 1ull : 0ull; }
+};
+template <typename Cand> struct EmitCand {
+    Cand c;
     int32_t *cpos;
     int32_t *cend;
     int64_t step;
@@ -300,7 +309,7 @@ struct EmitCand {
     {
         if (!cnt) return;
         cpos[excl] = (int32_t)i;
-        cend[excl] = (int32_t)would_emit(p, i);
+        cend[excl] = (int32_t)c(i);
         ckey[excl] = ((unsigned long long)(i % step) << abits) | (unsigned long long)i;
         cidx[excl] = (uint32_t)excl;
     }
@@ -320,9 +329,9 @@ __device__ __forceinline__ int64_t lower_bound(const unsigned long long *key, in
 // candidate visited first when the scan (re)starts at position s: smallest
 // candidate position >= s congruent to s modulo step
 __device__ __forceinline__ int32_t next_cand(const unsigned long long *skey, const uint32_t *sidx, int64_t K,
-                                             int64_t s, int64_t step, int abits, int64_t n, int m)
+                                             int64_t s, int64_t step, int abits, int64_t limit)
 {
-    if (s >= n - m) return -1;
+    if (s >= limit) return -1;  // the reference's scan loop has ended
     unsigned long long r = (unsigned long long)(s % step);
     int64_t at = lower_bound(skey, K, (r << abits) | (unsigned long long)s);
     if (at >= K) return -1;
@@ -331,13 +340,13 @@ __device__ __forceinline__ int32_t next_cand(const unsigned long long *skey, con
 }
 
 __global__ void succ_kernel(const int32_t *__restrict__ cend, const unsigned long long *__restrict__ skey,
-                            const uint32_t *__restrict__ sidx, int64_t K, int64_t step, int abits, int64_t n,
-                            int m, int32_t *__restrict__ succ, int32_t *__restrict__ first)
+                            const uint32_t *__restrict__ sidx, int64_t K, int64_t step, int abits,
+                            int64_t limit, int32_t *__restrict__ succ, int32_t *__restrict__ first)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k == 0) *first = next_cand(skey, sidx, K, 0, step, abits, n, m);
+    if (k == 0) *first = next_cand(skey, sidx, K, 0, step, abits, limit);
     if (k >= K) return;
-    succ[k] = next_cand(skey, sidx, K, cend[k], step, abits, n, m);
+    succ[k] = next_cand(skey, sidx, K, cend[k], step, abits, limit);
 }
 
 __global__ void double_kernel(const int32_t *__restrict__ jin, int32_t *__restrict__ jout, int64_t K)
@@ -378,24 +387,171 @@ struct CountPath {
     const uint8_t *onpath;
     __device__ uint64_t operator()(int64_t k) const { return onpath[k]; }
 };
-struct EmitPath {
+// Writer: __device__ void operator()(int64_t start, int64_t end, int32_t *row)
+template <typename Writer> struct EmitPath {
     const int32_t *cpos;
     const int32_t *cend;
-    int m;
+    Writer w;
     int32_t *rec;
     int64_t rec_base;
     int64_t cap;
-    uint8_t *seen;
     __device__ void operator()(int64_t k, uint64_t excl, uint64_t cnt) const
     {
         if (!cnt) return;
-        int32_t s = cpos[k], e = cend[k];
-        for (int32_t q = s; q < e; q++) seen[q] = 1;
         int64_t slot = rec_base + (int64_t)excl;
-        if (slot >= cap) return;
-        int32_t *row = rec + slot * BWTK_REC_W;
-        row[0] = s; row[1] = e; row[2] = m; row[3] = (e - s) / m;
+        int32_t row[BWTK_REC_W];
+        w(cpos[k], cend[k], row);   // side effects (seen mask) happen even past the capacity
+        if (slot < cap) {
+            int32_t *dst = rec + slot * BWTK_REC_W;
+#pragma unroll
+            for (int q = 0; q < BWTK_REC_W; q++) dst[q] = row[q];
+        }
+    }
+};
+
+struct Tier1Writer {
+    int m;
+    uint8_t *seen;
+    __device__ void operator()(int64_t s, int64_t e, int32_t *row) const
+    {
+        for (int64_t q = s; q < e; q++) seen[q] = 1;
+        row[0] = (int32_t)s; row[1] = (int32_t)e; row[2] = m; row[3] = (int32_t)((e - s) / m);
         row[4] = 0; row[5] = 0; row[6] = 0; row[7] = 0;
+    }
+};
+
+// scratch shared by the passes of one call
+struct PassWs {
+    int32_t *cpos, *cend, *succ, *j0, *j1, *anchor;
+    uint32_t *cidx0, *cidx1;
+    unsigned long long *ckey0, *ckey1;
+    uint8_t *onpath;
+    int32_t *d_first;
+    unsigned *d_nanchor;
+    rsort::Workspace rws;
+    scan::Workspace sws;
+};
+
+static int64_t pass_ws_bytes(int64_t n)
+{
+    return 8 * align_up(n * 4, 256) + 2 * align_up(n * 8, 256) + align_up(n, 256) + rsort::workspace_bytes(n) +
+           scan::workspace_bytes(n) + 4096;
+}
+
+static PassWs carve_pass_ws(Carver &c, int64_t n)
+{
+    PassWs w;
+    w.cpos = c.take<int32_t>(n); w.cend = c.take<int32_t>(n);
+    w.cidx0 = c.take<uint32_t>(n); w.cidx1 = c.take<uint32_t>(n);
+    w.succ = c.take<int32_t>(n); w.j0 = c.take<int32_t>(n); w.j1 = c.take<int32_t>(n);
+    w.anchor = c.take<int32_t>(n);
+    w.ckey0 = c.take<unsigned long long>(n); w.ckey1 = c.take<unsigned long long>(n);
+    w.onpath = c.take<uint8_t>(n);
+    w.rws = rsort::carve(c, n);
+    w.sws = scan::carve(c, n);
+    w.d_first = c.take<int32_t>(4);
+    w.d_nanchor = c.take<unsigned>(4);
+    return w;
+}
+
+// One greedy pass: positions [0, npos) are scanned with stride `step`, an emission
+// at c jumps to end(c); the scan stops at `limit`.  Appends rows at rec_base and
+// returns the number of emissions in *emitted.
+template <typename Cand, typename Writer>
+static int greedy_pass(int64_t npos, int64_t limit, int64_t step, int abits, Cand cand, Writer writer,
+                       const PassWs &w, int32_t *d_rec, int64_t rec_base, int64_t cap, int64_t *emitted,
+                       cudaStream_t st)
+{
+    *emitted = 0;
+    if (npos <= 0) return BWTK_OK;
+    CountCand<Cand> cc{cand};
+    EmitCand<Cand> ec{cand, w.cpos, w.cend, step, abits, w.ckey0, w.cidx0};
+    int rc = scan::run(npos, cc, ec, w.sws, st);
+    if (rc) return rc;
+    unsigned long long hK = 0;
+    BWTK_CUDA(cudaMemcpyAsync(&hK, w.sws.total, 8, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    int64_t K = (int64_t)hK;
+    if (K == 0) return BWTK_OK;
+    const unsigned long long *skey = w.ckey0;
+    const uint32_t *sidx = w.cidx0;
+    if (step > 1) {
+        int in_first = 1;
+        int sbits = 1;
+        while ((1ll << sbits) <= step) sbits++;
+        rc = rsort::sort_pairs<unsigned long long>(w.ckey0, w.cidx0, w.ckey1, w.cidx1, K, 0, abits + sbits, w.rws, st,
+                                                   &in_first, nullptr);
+        if (rc) return rc;
+        skey = in_first ? w.ckey0 : w.ckey1;
+        sidx = in_first ? w.cidx0 : w.cidx1;
+    }
+    succ_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(w.cend, skey, sidx, K, step, abits, limit, w.succ,
+                                                          w.d_first);
+    BWTK_LAUNCH_CHECK();
+    // jump table for 2^kappa hops, kappa ~ log2(K)/2
+    int kappa = 0;
+    while ((1ll << (2 * kappa)) < K) kappa++;
+    const int32_t *jbig = w.succ;
+    int32_t *ja = w.j0, *jb = w.j1;
+    for (int r = 0; r < kappa; r++) {
+        double_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(jbig, ja, K);
+        BWTK_LAUNCH_CHECK();
+        jbig = ja;
+        int32_t *t = ja; ja = jb; jb = t;
+    }
+    coarse_walk_kernel<<<1, 32, 0, st>>>(jbig, w.d_first, w.anchor, w.d_nanchor);
+    BWTK_LAUNCH_CHECK();
+    BWTK_CUDA(cudaMemsetAsync(w.onpath, 0, (size_t)K, st));
+    int64_t max_anchor = (K >> kappa) + 2;
+    fine_walk_kernel<<<(unsigned)ceil_div(max_anchor, 128), 128, 0, st>>>(w.succ, w.anchor, w.d_nanchor,
+                                                                        1ll << kappa, w.onpath);
+    BWTK_LAUNCH_CHECK();
+    CountPath cp{w.onpath};
+    EmitPath<Writer> ep{w.cpos, w.cend, writer, d_rec, rec_base, cap};
+    rc = scan::run(K, cp, ep, w.sws, st);
+    if (rc) return rc;
+    unsigned long long hE = 0;
+    BWTK_CUDA(cudaMemcpyAsync(&hE, w.sws.total, 8, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    *emitted = (int64_t)hE;
+    return BWTK_OK;
+}
+
+// ---- strict adjacency with max_mismatch > 0 (bwt.py:1921-1999) -------------------
+struct StrictMMCand {
+    const uint8_t *text;
+    int64_t n;   // without the trailing '$'
+    int64_t u, mm, mc;
+    __device__ int64_t operator()(int64_t i) const
+    {
+        if (i + u * mc > n) return -1;
+        int64_t count = 1;
+        for (;;) {
+            int64_t a = i + (count - 1) * u, b = i + count * u;
+            if (b + u > n) break;
+            int64_t hd = 0;
+            for (int64_t t = 0; t < u && hd <= mm; t++) hd += (__ldg(text + a + t) != __ldg(text + b + t));
+            if (hd <= mm) count++; else break;
+        }
+        return count >= mc ? i + count * u : -1;
+    }
+};
+struct StrictMMWriter {
+    const uint8_t *text;
+    int64_t u;
+    __device__ void operator()(int64_t s, int64_t e, int32_t *row) const
+    {
+        int64_t prim = u;
+        for (int64_t p = 1; p <= u / 2; p++) {
+            if (u % p) continue;
+            bool ok = true;
+            for (int64_t j = p; j < u; j++)
+                if (__ldg(text + s + j) != __ldg(text + s + j - p)) { ok = false; break; }
+            if (ok) { prim = p; break; }
+        }
+        row[0] = (int32_t)s; row[1] = (int32_t)e; row[2] = (int32_t)prim;
+        row[3] = (int32_t)(prim < u ? (e - s) / prim : (e - s) / u);
+        row[4] = 0; row[5] = 0; row[6] = (int32_t)u; row[7] = 0;
     }
 };
 
@@ -498,9 +654,11 @@ extern "C" int64_t bwtk_strict_workspace_bytes(int64_t n, int64_t)
 {
     if (n < 1) n = 1;
     int64_t cap = strict::cand_capacity(n);
-    return 2 * align_up(cap * 8, 256) + 2 * align_up(cap * 4, 256) + align_up(cap, 256) +
-           align_up(cap * BWTK_REC_W * 4, 256) + rsort::workspace_bytes(cap) + scan::workspace_bytes(cap) +
-           8192;
+    int64_t exact = 2 * align_up(cap * 8, 256) + 2 * align_up(cap * 4, 256) + align_up(cap, 256) +
+                    align_up(cap * BWTK_REC_W * 4, 256) + rsort::workspace_bytes(cap) + scan::workspace_bytes(cap) +
+                    8192;
+    int64_t general = tier1::pass_ws_bytes(n) + 8192;  // max_mismatch > 0: greedy replay per unit length
+    return exact > general ? exact : general;
 }
 
 extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int64_t min_unit_len,
@@ -513,7 +671,7 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
     *h_count = 0;
     BWTK_REQUIRE(min_copies >= 2, "min_copies must be >= 2");
     BWTK_REQUIRE(min_unit_len >= 1, "min_unit_len must be >= 1");
-    BWTK_REQUIRE(max_mismatch == 0, "device strict scan implements max_mismatch == 0 (the CLI's setting)");
+    BWTK_REQUIRE(max_mismatch >= 0, "max_mismatch must be >= 0");
     if (n_total <= 0) return BWTK_OK;
     BWTK_REQUIRE(d_text && d_ws && (d_rec || cap == 0), "null pointer");
     BWTK_REQUIRE(n_total < (1ll << 30), "n must be < 2^30");
@@ -530,6 +688,38 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
     if (ws_bytes < bwtk_strict_workspace_bytes(n_total, max_unit_len)) {
         set_error("strict workspace: need %lld bytes", (long long)bwtk_strict_workspace_bytes(n_total, max_unit_len));
         return BWTK_EWORKSPACE;
+    }
+    if (max_mismatch > 0) {
+        // Hamming-tolerant adjacency: candidates "count(i) >= min_copies" per unit
+        // length, greedy order replayed by pointer jumping (same engine as Tier 1).
+        Carver cg(d_ws, ws_bytes);
+        tier1::PassWs pw = tier1::carve_pass_ws(cg, n_total);
+        if (!cg.ok()) { set_error("strict workspace carve overflow"); return BWTK_EWORKSPACE; }
+        BWTK_CUDA(cudaMemsetAsync(pw.rws.err, 0, sizeof(int), st));
+        BWTK_CUDA(cudaMemsetAsync(pw.sws.err, 0, sizeof(int), st));
+        const int abits_g = strict::bits_for(n);
+        int64_t total = 0;
+        for (int64_t u = umax; u >= min_unit_len; u--) {
+            int64_t npos = n - u * min_copies + 1;  // positions the while-loop can visit
+            if (npos <= 0) continue;
+            tier1::StrictMMCand cand{d_text, n, u, max_mismatch, min_copies};
+            tier1::StrictMMWriter wr{d_text, u};
+            int64_t emitted = 0;
+            int rc = tier1::greedy_pass(npos, npos, 1, abits_g, cand, wr, pw, d_rec, total, cap, &emitted, st);
+            if (rc) return rc;
+            total += emitted;
+        }
+        int h_err[2] = {0, 0};
+        BWTK_CUDA(cudaMemcpyAsync(&h_err[0], pw.rws.err, 4, cudaMemcpyDeviceToHost, st));
+        BWTK_CUDA(cudaMemcpyAsync(&h_err[1], pw.sws.err, 4, cudaMemcpyDeviceToHost, st));
+        BWTK_CUDA(cudaStreamSynchronize(st));
+        if (h_err[0] || h_err[1]) { set_error("look-back spin limit hit in strict scan"); return BWTK_EINTERNAL; }
+        *h_count = total;
+        if (total > cap) {
+            set_error("strict scan: %lld records exceed capacity %lld", (long long)total, (long long)cap);
+            return BWTK_EOVERFLOW;
+        }
+        return BWTK_OK;
     }
     const int64_t ccap = strict::cand_capacity(n_total);
     Carver c(d_ws, ws_bytes);
@@ -627,9 +817,7 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
 extern "C" int64_t bwtk_tier1_workspace_bytes(int64_t n)
 {
     if (n < 1) n = 1;
-    // seen + (cpos,cend,cidx,cidx2,succ,j0,j1,anchor) + (ckey x2) + onpath + sort/scan scratch + entropy table
-    return align_up(n, 256) + 8 * align_up(n * 4, 256) + 2 * align_up(n * 8, 256) + align_up(n, 256) +
-           rsort::workspace_bytes(n) + scan::workspace_bytes(n) + 8192;
+    return align_up(n, 256) + tier1::pass_ws_bytes(n) + 8192;  // seen mask + pass scratch + entropy table
 }
 
 extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max_motif_len,
@@ -650,26 +838,12 @@ extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max
     }
     Carver c(d_ws, ws_bytes);
     uint8_t *seen = c.take<uint8_t>(n);
-    int32_t *cpos = c.take<int32_t>(n);
-    int32_t *cend = c.take<int32_t>(n);
-    uint32_t *cidx0 = c.take<uint32_t>(n);
-    uint32_t *cidx1 = c.take<uint32_t>(n);
-    int32_t *succ = c.take<int32_t>(n);
-    int32_t *j0 = c.take<int32_t>(n);
-    int32_t *j1 = c.take<int32_t>(n);
-    int32_t *anchor = c.take<int32_t>(n);
-    unsigned long long *ckey0 = c.take<unsigned long long>(n);
-    unsigned long long *ckey1 = c.take<unsigned long long>(n);
-    uint8_t *onpath = c.take<uint8_t>(n);
-    rsort::Workspace rws = rsort::carve(c, n);
-    scan::Workspace sws = scan::carve(c, n);
+    tier1::PassWs pw = tier1::carve_pass_ws(c, n);
     double *d_plogp = c.take<double>(100);
-    int32_t *d_first = c.take<int32_t>(4);
-    unsigned *d_nanchor = c.take<unsigned>(4);
     if (!c.ok()) { set_error("tier1 workspace carve overflow"); return BWTK_EWORKSPACE; }
     BWTK_CUDA(cudaMemsetAsync(seen, 0, (size_t)n, st));
-    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
-    BWTK_CUDA(cudaMemsetAsync(sws.err, 0, sizeof(int), st));
+    BWTK_CUDA(cudaMemsetAsync(pw.rws.err, 0, sizeof(int), st));
+    BWTK_CUDA(cudaMemsetAsync(pw.sws.err, 0, sizeof(int), st));
     // (c/L)*log2(c/L) in IEEE double, the same expression the host evaluates
     double plogp[100];
     for (int L = 0; L < 10; L++)
@@ -681,67 +855,24 @@ extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max
     BWTK_CUDA(cudaMemcpyAsync(d_plogp, plogp, sizeof(plogp), cudaMemcpyHostToDevice, st));
     BWTK_CUDA(cudaStreamSynchronize(st));
 
+    // adaptive sampling of the reference (bwt.py:1441-1448)
     int64_t step = n > 10000000 ? 50 : (n > 5000000 ? 20 : 1);
     const int abits = strict::bits_for(n);
-    const int sbits = strict::bits_for(step);
     int64_t total = 0;
     int mmax = max_motif_len < 9 ? max_motif_len : 9;
     for (int m = mmax; m >= 1; m--) {
         if (n - m <= 0) continue;
         tier1::Params p{d_text, seen, n, m, min_copies, min_array_len, min_entropy, d_plogp};
-        tier1::CountCand cc{p};
-        tier1::EmitCand ec{p, cpos, cend, step, abits, ckey0, cidx0};
-        int rc = scan::run(n - m, cc, ec, sws, st);
+        tier1::Tier1Cand cand{p};
+        tier1::Tier1Writer wr{m, seen};
+        int64_t emitted = 0;
+        int rc = tier1::greedy_pass(n - m, n - m, step, abits, cand, wr, pw, d_rec, total, cap, &emitted, st);
         if (rc) return rc;
-        unsigned long long hK = 0;
-        BWTK_CUDA(cudaMemcpyAsync(&hK, sws.total, 8, cudaMemcpyDeviceToHost, st));
-        BWTK_CUDA(cudaStreamSynchronize(st));
-        int64_t K = (int64_t)hK;
-        if (K == 0) continue;
-        const unsigned long long *skey = ckey0;
-        const uint32_t *sidx = cidx0;
-        if (step > 1) {
-            int in_first = 1;
-            rc = rsort::sort_pairs<unsigned long long>(ckey0, cidx0, ckey1, cidx1, K, 0, abits + sbits, rws, st,
-                                                       &in_first, nullptr);
-            if (rc) return rc;
-            skey = in_first ? ckey0 : ckey1;
-            sidx = in_first ? cidx0 : cidx1;
-        }
-        tier1::succ_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(cend, skey, sidx, K, step, abits, n, m,
-                                                                     succ, d_first);
-        BWTK_LAUNCH_CHECK();
-        // jump table for 2^kappa hops, kappa ~ log2(K)/2
-        int kappa = 0;
-        while ((1ll << (2 * kappa)) < K) kappa++;
-        const int32_t *jbig = succ;
-        int32_t *ja = j0, *jb = j1;
-        for (int r = 0; r < kappa; r++) {
-            tier1::double_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(jbig, ja, K);
-            BWTK_LAUNCH_CHECK();
-            jbig = ja;
-            int32_t *t = ja; ja = jb; jb = t;
-        }
-        tier1::coarse_walk_kernel<<<1, 32, 0, st>>>(jbig, d_first, anchor, d_nanchor);
-        BWTK_LAUNCH_CHECK();
-        BWTK_CUDA(cudaMemsetAsync(onpath, 0, (size_t)K, st));
-        // at most ceil(K / 2^kappa) + 1 anchors
-        int64_t max_anchor = (K >> kappa) + 2;
-        tier1::fine_walk_kernel<<<(unsigned)ceil_div(max_anchor, 128), 128, 0, st>>>(succ, anchor, d_nanchor,
-                                                                                   1ll << kappa, onpath);
-        BWTK_LAUNCH_CHECK();
-        tier1::CountPath cp{onpath};
-        tier1::EmitPath ep{cpos, cend, m, d_rec, total, cap, seen};
-        rc = scan::run(K, cp, ep, sws, st);
-        if (rc) return rc;
-        unsigned long long hE = 0;
-        BWTK_CUDA(cudaMemcpyAsync(&hE, sws.total, 8, cudaMemcpyDeviceToHost, st));
-        BWTK_CUDA(cudaStreamSynchronize(st));
-        total += (int64_t)hE;
+        total += emitted;
     }
     int h_err[2] = {0, 0};
-    BWTK_CUDA(cudaMemcpyAsync(&h_err[0], rws.err, 4, cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaMemcpyAsync(&h_err[1], sws.err, 4, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaMemcpyAsync(&h_err[0], pw.rws.err, 4, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaMemcpyAsync(&h_err[1], pw.sws.err, 4, cudaMemcpyDeviceToHost, st));
     if (d_seen_out) BWTK_CUDA(cudaMemcpyAsync(d_seen_out, seen, (size_t)n, cudaMemcpyDeviceToDevice, st));
     BWTK_CUDA(cudaStreamSynchronize(st));
     if (h_err[0] || h_err[1]) { set_error("look-back spin limit hit in tier1 scan"); return BWTK_EINTERNAL; }

@@ -38,6 +38,76 @@ def _device_text_of(bwt_core):
     return bwt_core.text_arr
 
 
+# ---------------------------------------------------------------------------
+# integer rows (kernels) -> TandemRepeat records (host floats, bwt.py formulas)
+# ---------------------------------------------------------------------------
+def tier1_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str) -> List[TandemRepeat]:
+    """Rows (start,end,motif_len,copies) -> Tier 1 records (bwt.py:1493-1522)."""
+    out: List[TandemRepeat] = []
+    for start, end, m, copies in rows[:, :4].tolist():
+        motif = _decode(text_arr, start, start + m)
+        pm, pi, score, comp, ent, _ = MotifUtils.calculate_trf_statistics(text_arr, start, end, motif, copies, 0.0)
+        out.append(TandemRepeat(
+            chrom=chromosome, start=start, end=end, motif=motif, copies=float(copies), length=end - start,
+            tier=1, confidence=1.0, consensus_motif=motif, mismatch_rate=0.0, max_mismatches_per_copy=0,
+            n_copies_evaluated=copies, strand="+", percent_matches=pm, percent_indels=pi, score=score,
+            composition=comp, entropy=ent, actual_sequence=_decode(text_arr, start, end), variations=None))
+    return out
+
+
+def strict_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str, max_mismatch: int) -> List[TandemRepeat]:
+    """Rows (start,end,primitive_period,copies) -> strict-scan records (bwt.py:1951-1996)."""
+    out: List[TandemRepeat] = []
+    for start, end, prim, count in rows[:, :4].tolist():
+        motif = _decode(text_arr, start, start + prim)
+        pm, pi, score, comp, ent, actual = MotifUtils.calculate_trf_statistics(text_arr, start, end, motif, count, 0.0)
+        out.append(TandemRepeat(
+            chrom=chromosome, start=start, end=end, motif=motif, copies=float(count), length=end - start,
+            tier=2, confidence=0.95, consensus_motif=motif, mismatch_rate=0.0,
+            max_mismatches_per_copy=(0 if pm >= 99.9 else max_mismatch), n_copies_evaluated=count, strand="+",
+            percent_matches=pm, percent_indels=pi, score=score, composition=comp, entropy=ent,
+            actual_sequence=actual, variations=None))
+    return out
+
+
+def plateau_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str) -> List[TandemRepeat]:
+    """Rows (start,end,period,copies) -> LCP-plateau records (bwt.py:2536-2547);
+    coordinates are numpy int32 scalars as in the reference."""
+    out: List[TandemRepeat] = []
+    for start, end, period, copies in rows[:, :4].tolist():
+        out.append(TandemRepeat(chrom=chromosome, start=np.int32(start), end=np.int32(end),
+                                motif=_decode(text_arr, start, start + period), copies=copies,
+                                length=copies * period, tier=2, confidence=0.9))
+    return out
+
+
+def period_records(s_arr: np.ndarray, rows: np.ndarray, cons_list, chromosome: str) -> List[TandemRepeat]:
+    """Period-scan rows + consensus bytes -> records, with the (start,end,canonical)
+    dedup of bwt.py:2343-2385."""
+    out: List[TandemRepeat] = []
+    seen: Set[Tuple[int, int, str]] = set()
+    for row, cons_arr in zip(rows.tolist(), cons_list):
+        a_start, a_end, p_eff, copies_full, total_mm, max_mm, _cons_start, used = row
+        cons = cons_arr.tobytes().decode("ascii", errors="replace")
+        cells = used * p_eff
+        mm_rate = total_mm / cells if cells > 0 else 0.0
+        canonical, strand = MotifUtils.get_canonical_motif_stranded(cons)
+        key = (a_start, a_end, canonical)
+        if key in seen:
+            continue
+        seen.add(key)
+        pm, pi, score, comp, ent, actual = MotifUtils.calculate_trf_statistics(
+            s_arr, a_start, a_end, cons, copies_full, mm_rate)
+        notes = MotifUtils.summarize_variations_array(s_arr, a_start, a_end, p_eff, cons_arr)
+        out.append(TandemRepeat(
+            chrom=chromosome, start=a_start, end=a_end, motif=cons, copies=float(copies_full),
+            length=a_end - a_start, tier=2, confidence=max(0.5, 0.95 - mm_rate), consensus_motif=cons,
+            mismatch_rate=mm_rate, max_mismatches_per_copy=max_mm, n_copies_evaluated=copies_full,
+            strand=strand, percent_matches=pm, percent_indels=pi, score=score, composition=comp, entropy=ent,
+            actual_sequence=actual, variations=notes if notes else None))
+    return out
+
+
 class Tier1STRFinder:
     """Perfect short tandem repeats, motif length 9..1 (bwt.py:1387-1538)."""
 
@@ -59,16 +129,7 @@ class Tier1STRFinder:
             print(f"  [{chromosome}] Large sequence ({n:,} bp) - using fast sampling mode (step=50)")
         rows = detect.tier1_rows(text_arr, self.max_motif_length, self.min_copies, self.min_array_length,
                                  self.min_entropy)
-        out: List[TandemRepeat] = []
-        for start, end, m, copies in rows[:, :4].tolist():
-            motif = _decode(text_arr, start, start + m)
-            pm, pi, score, comp, ent, _ = MotifUtils.calculate_trf_statistics(text_arr, start, end, motif, copies, 0.0)
-            out.append(TandemRepeat(
-                chrom=chromosome, start=start, end=end, motif=motif, copies=float(copies), length=end - start,
-                tier=1, confidence=1.0, consensus_motif=motif, mismatch_rate=0.0, max_mismatches_per_copy=0,
-                n_copies_evaluated=copies, strand="+", percent_matches=pm, percent_indels=pi, score=score,
-                composition=comp, entropy=ent, actual_sequence=_decode(text_arr, start, end), variations=None))
-        return out
+        return tier1_records(text_arr, rows, chromosome)
 
     def find_strs(self, chromosome: str) -> List[TandemRepeat]:
         return self._find_simple_tandems_kmer(chromosome)
@@ -122,17 +183,7 @@ class Tier2LCPFinder:
                                       max_mismatch: int = 2, min_copies: int = 3) -> List[TandemRepeat]:
         text_arr = self.bwt.text_arr
         rows = detect.strict_rows(_device_text_of(self.bwt), min_unit_len, max_unit_len, max_mismatch, min_copies)
-        out: List[TandemRepeat] = []
-        for start, end, prim, count in rows[:, :4].tolist():
-            motif = _decode(text_arr, start, start + prim)
-            pm, pi, score, comp, ent, actual = MotifUtils.calculate_trf_statistics(text_arr, start, end, motif, count, 0.0)
-            out.append(TandemRepeat(
-                chrom=chromosome, start=start, end=end, motif=motif, copies=float(count), length=end - start,
-                tier=2, confidence=0.95, consensus_motif=motif, mismatch_rate=0.0,
-                max_mismatches_per_copy=(0 if pm >= 99.9 else max_mismatch), n_copies_evaluated=count, strand="+",
-                percent_matches=pm, percent_indels=pi, score=score, composition=comp, entropy=ent,
-                actual_sequence=actual, variations=None))
-        return out
+        return strict_records(text_arr, rows, chromosome, max_mismatch)
 
     # ---- a10 / a15: LCP array and plateaus --------------------------------------
     def _compute_lcp_array(self) -> np.ndarray:
@@ -149,12 +200,7 @@ class Tier2LCPFinder:
         lcp = np.ascontiguousarray(lcp_array, np.int32)  # the caller's array is authoritative
         rows, _thr = detect.plateau_rows(_device_text_of(self.bwt), sa, lcp, self.min_period, self.max_period,
                                          self.min_copies)
-        out: List[TandemRepeat] = []
-        for start, end, period, copies in rows[:, :4].tolist():
-            out.append(TandemRepeat(chrom=chromosome, start=np.int32(start), end=np.int32(end),
-                                    motif=_decode(text_arr, start, start + period), copies=copies,
-                                    length=copies * period, tier=2, confidence=0.9))
-        return out
+        return plateau_records(text_arr, rows, chromosome)
 
     def _analyze_sa_interval_for_tandems(self, start_idx: int, end_idx: int, period: int,
                                          chromosome: str) -> List[TandemRepeat]:
@@ -202,28 +248,7 @@ class Tier2LCPFinder:
         if len(rows) == 0:
             return []
         cons_list, _mm = detect.consensus_batch(text_dev, rows[:, 6], rows[:, 2], rows[:, 3])
-        out: List[TandemRepeat] = []
-        seen: Set[Tuple[int, int, str]] = set()
-        for row, cons_arr in zip(rows.tolist(), cons_list):
-            a_start, a_end, p_eff, copies_full, total_mm, max_mm, _cons_start, used = row
-            cons = cons_arr.tobytes().decode("ascii", errors="replace")
-            cells = used * p_eff
-            mm_rate = total_mm / cells if cells > 0 else 0.0
-            canonical, strand = MotifUtils.get_canonical_motif_stranded(cons)
-            key = (a_start, a_end, canonical)
-            if key in seen:
-                continue
-            seen.add(key)
-            pm, pi, score, comp, ent, actual = MotifUtils.calculate_trf_statistics(
-                s_arr, a_start, a_end, cons, copies_full, mm_rate)
-            notes = MotifUtils.summarize_variations_array(s_arr, a_start, a_end, p_eff, cons_arr)
-            out.append(TandemRepeat(
-                chrom=chromosome, start=a_start, end=a_end, motif=cons, copies=float(copies_full),
-                length=a_end - a_start, tier=2, confidence=max(0.5, 0.95 - mm_rate), consensus_motif=cons,
-                mismatch_rate=mm_rate, max_mismatches_per_copy=max_mm, n_copies_evaluated=copies_full,
-                strand=strand, percent_matches=pm, percent_indels=pi, score=score, composition=comp, entropy=ent,
-                actual_sequence=actual, variations=notes if notes else None))
-        return out
+        return period_records(s_arr, rows, cons_list, chromosome)
 
     # ---- a14: FM / k-mer seeded seed-and-extend ------------------------------------
     def _extend_tandem_fm(self, text_arr: np.ndarray, seed_pos: int, motif: str, motif_len: int,

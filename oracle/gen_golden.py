@@ -243,6 +243,15 @@ def cases():
     cs.append(("adv_Nruns", "ACGT" * 10 + "N" * 50 + "ACGTTGCA" * 8 + "N" * 9 + "GATTACA" * 6, 2))
     cs.append(("adv_iupac", "ACGTRYACGTACGTKMACGTACGTACGTSWACGTNNACGTACGTACGTACGT" * 3, 1))
     cs.append(("adv_period3", "CAG" * 120 + "T" + "CAG" * 60, 2))
+    # seeded seed-and-extend (a14) cases that actually yield records
+    rng = np.random.default_rng(77)
+    rnd = lambda n: "".join("ACGT"[x] for x in rng.integers(0, 4, n))
+    cs.append(("a14_k9_transition", rnd(60) + "GATTACAGG" * 4 + "GATTGCAGG" + "GATTACAGG" * 5 + rnd(50), 3))
+    cs.append(("a14_k8_two_loci", rnd(40) + "AACCGGTT" * 3 + "AACCAGTT" + "AACCGGTT" * 4 + rnd(30)
+               + "ACGGTCAT" * 7 + rnd(35), 3))
+    cs.append(("a14_k7_aliased", rnd(30) + "AAGGCTC" * 9 + rnd(25) + "AAGGCTC" * 3 + "AAGACTC" + "AAGGCTC" * 4 + rnd(20), 3))
+    cs.append(("a14_mixed", rnd(50) + "AAAAAAACACACACACACACAC" + rnd(20) + "AAAAAAACAAAAAAAC" + "CAGCAGCAGCAACAGCAGCAGCAG"
+               + rnd(30) + "TTGACCGTA" * 6 + "TTGACTGTA" + "TTGACCGTA" * 3 + rnd(40), 3))
     cs.append(("adv_empty", "", 0))
     cs.append(("adv_one", "G", 0))
     return cs

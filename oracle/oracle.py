@@ -301,3 +301,127 @@ def period_scan(text_arr, min_period: int = 1, max_period: int = 1000, allow_mis
         _ptr(t), t.size, min_period, max_period, int(allow_mismatches), min_copies,
         min_array_length, min_entropy, _ptr(mask), _ptr(rec), cap, C.byref(it)))
     return rows, int(it.value)
+
+
+# ---------------------------------------------------------------- a14 (sequential restatement)
+_COMP = {"A": "T", "T": "A", "C": "G", "G": "C", "N": "N"}
+_BITS = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 0}
+
+
+def _canonical(m: str) -> str:
+    return min(m[i:] + m[:i] for i in range(len(m))) if m else m
+
+
+def _primitive(m: str) -> bool:
+    n = len(m)
+    return not any(n % p == 0 and m[:p] * (n // p) == m for p in range(1, n))
+
+
+def enumerate_motifs(k: int):
+    """bwt.py:1368-1381: canonical primitive motifs in lexicographic order."""
+    import itertools
+
+    for tup in itertools.product("ACGT", repeat=k):
+        m = "".join(tup)
+        if _canonical(m) == m and _primitive(m):
+            yield m
+
+
+def short_imperfect_arrays(text, tier1_seen=(), min_period: int = 1, max_short_motif: int = 9,
+                           min_copies: int = 3, min_array_length: int = 6, min_entropy: float = 1.0):
+    """bwt.py:2027-2095 + 2562-2695, walked seed by seed exactly as written.
+    Returns accepted arrays (start, end, motif_len, copies, consensus, total_mm, max_mm, used)."""
+    t = _u8(text)
+    n = int(t.size)
+    if n > 1_000_000:
+        return []
+    ix = OracleIndex(t)
+    table = kmer8_table(t)
+    seen = set(tuple(x) for x in tier1_seen)
+    out = []
+
+    def locate(pat: str):
+        sp, ep = ix.backward_search(pat)
+        return [] if sp == -1 else sorted(int(x) for x in ix.sa[sp:ep + 1])
+
+    def kmer_positions(kmer: str):
+        if len(kmer) > 8 or not table:
+            return locate(kmer)
+        w = 0
+        for b in kmer.upper():
+            if b not in _BITS:
+                return []
+            w = (w << 2) | _BITS[b]
+        return table.get(w, [])
+
+    for k in range(min_period, min(max_short_motif + 1, 10)):
+        motifs = [m for m in enumerate_motifs(k) if not (entropy(m) < min_entropy)]
+        rot_sets = []
+        for motif in motifs:
+            rc = "".join(_COMP.get(b, b) for b in reversed(motif))
+            rot_sets.append(sorted(set([motif[i:] + motif[:i] for i in range(k)] + [rc[i:] + rc[:i] for i in range(k)])))
+        fm_hits = {}
+        if k > 8 and motifs:
+            # the same backward searches the reference issues one by one (bwt.py:2078-2079), batched
+            flat = [r for rs in rot_sets for r in rs]
+            mat = np.frombuffer("".join(flat).encode(), np.uint8).reshape(len(flat), k)
+            bsp, bep = ix.backward_search_batch(mat, np.full(len(flat), k, np.int32))
+            for r, a, b in zip(flat, bsp.tolist(), bep.tolist()):
+                if a != -1:
+                    fm_hits[r] = (a, b)
+        for motif, rots in zip(motifs, rot_sets):
+            allpos = []
+            for r in rots:
+                if k <= 8:
+                    allpos.extend(kmer_positions(r))
+                elif r in fm_hits:
+                    a, b = fm_hits[r]
+                    allpos.extend(int(x) for x in ix.sa[a:b + 1])
+            positions = sorted(set(allpos))
+            if len(positions) < min_copies:
+                continue
+            motif_len = k
+            for seed in positions:
+                if any(a <= seed < b for a, b in seen):
+                    continue
+                if seed + motif_len > n:
+                    continue
+                best = None
+                for shift in range(min(motif_len, seed + 1)):
+                    cand = seed - shift
+                    if cand < 0 or cand + motif_len > n:
+                        continue
+                    if any(a <= cand < b for a, b in seen):
+                        continue
+                    s, e, c = extend_tandem_fm(t, cand, motif_len)
+                    if not (s <= seed < e):
+                        continue
+                    if best is None or c > best[2] or (c == best[2] and s < best[0]):
+                        best = (s, e, c)
+                if best is None:
+                    continue
+                start, end, copies = best
+                if not (copies >= min_copies and end - start >= min_array_length):
+                    continue
+                cons, rate, mx = consensus(t, start, motif_len, copies)
+                if cons.size == 0:
+                    continue
+                prim = smallest_period(cons)
+                if prim < cons.size:
+                    motif_len = prim
+                    copies = max(1, (end - start) // motif_len)
+                    end = start + copies * motif_len
+                    cons, rate, mx = consensus(t, start, motif_len, copies)
+                    if cons.size == 0:
+                        continue
+                if start > 0 and t[start - 1] == cons[motif_len - 1]:
+                    continue
+                if end < n and t[end] == cons[0]:
+                    continue
+                if (1.0 - rate) * 100.0 < (90.0 if motif_len <= 6 else 85.0):
+                    continue
+                used = copies
+                total_mm = int(round(rate * used * motif_len))
+                out.append((start, end, motif_len, copies, cons, total_mm, mx, used))
+                seen.add((start, end))
+    return out

@@ -1,0 +1,92 @@
+"""End-to-end record identity with the reference CLI.
+
+tests/golden/cli/ holds the output files of the UNMODIFIED reference CLI on its
+own FASTA fixtures for all five formats (oracle/gen_cli_golden.py; the default
+run on test.fa equals the reference's own repeat.tab).
+
+  * CPU test: the host glue alone -- FASTA loading, post-processing chain and
+    writers -- fed with raw records from the CPU oracle's strict scan.
+  * GPU test: the real thing, `bwt.main([...])`, byte for byte.
+"""
+import os
+
+import numpy as np
+import pytest
+
+CLI = os.path.join(os.path.dirname(__file__), "golden", "cli")
+CASES = [
+    ("test.fa", [], "test"),
+    ("test.fa", ["--tier1"], "test_tier1"),
+    ("test2.fa", [], "test2"),
+    ("test2.fa", ["--max-motif-len", "12"], "test2_max-motif-len_12"),
+    ("test_long_motif.fa", [], "test_long_motif"),
+    ("test_synthetic.fasta", ["--flank-trim", "0"], "test_synthetic_flank-trim_0"),
+]
+FORMATS = ["strfinder", "bed", "vcf", "trf_table", "trf_dat"]
+
+
+def _expected(tag, fmt):
+    with open(os.path.join(CLI, f"{tag}.{fmt}.txt")) as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("fa,flags,tag", CASES, ids=[c[2] for c in CASES])
+def test_host_glue_reproduces_reference_outputs(oracle, tmp_path, fa, flags, tag):
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200 import finders
+    from bwt_algorithm_b200.pipeline import TandemRepeatFinder
+
+    trim = 0 if "--flank-trim" in flags else 30
+    finder = TandemRepeatFinder(os.path.join(CLI, fa), flank_trim=trim,
+                                max_motif_length=12 if "--max-motif-len" in flags else 9)
+    seqs = finder.load_reference()
+    raw = []
+    if "--tier1" not in flags:
+        for chrom, seq in seqs.items():
+            text = (seq + "$").encode()
+            eff = max(120, min(len(seq) // 3, 1000))
+            rows = oracle.strict_scan(text, 1, eff, 0, 3)
+            raw.extend(finders.strict_records(np.frombuffer(text, np.uint8), rows, chrom, 0))
+    final, _dups = finder._postprocess(raw, lambda m: None)
+    for fmt in FORMATS:
+        out = tmp_path / f"{tag}.{fmt}"
+        finder.save_results(final, str(out), fmt)
+        assert out.read_text() == _expected(tag, fmt), f"{tag} ({fmt}) differs from the reference CLI output"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("jobs", ["-1", "4"])
+@pytest.mark.parametrize("fa,flags,tag", CASES, ids=[c[2] for c in CASES])
+def test_cli_byte_identical_on_gpu(tmp_path, capsys, fa, flags, tag, jobs):
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200 import bwt
+
+    for fmt in FORMATS:
+        out = tmp_path / f"{tag}.{fmt}"
+        bwt.main([os.path.join(CLI, fa), "-o", str(out), "--format", fmt, "--jobs", jobs] + flags)
+        assert out.read_text() == _expected(tag, fmt), f"{tag} ({fmt}, jobs {jobs}) differs"
+    capsys.readouterr()
+
+
+@pytest.mark.gpu
+def test_reference_unit_tests_on_gpu():
+    """The reference's own assertions (tests/test_repeat_outputs.py:36-62) through the drop-in."""
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200.bwt import TandemRepeatFinder
+
+    finder = TandemRepeatFinder(os.path.join(CLI, "test2.fa"), show_progress=False, max_motif_length=12)
+    finder.load_reference()
+    repeats = finder.find_tandem_repeats(enable_tier1=True, enable_tier2=True, enable_tier3=False)
+    by = {}
+    for r in repeats:
+        by.setdefault(r.chrom, []).append(r)
+    r1 = by["test1_PERFECT_7mer_5copies"][0]
+    assert (r1.start, r1.end, r1.motif, r1.copies, r1.variations) == (30, 65, "TCATCGG", 5.0, None)
+    assert len(by["test4_INTERRUPTED_7mer_11copies"]) == 1
+    r4 = by["test4_INTERRUPTED_7mer_11copies"][0]
+    assert r4.variations is not None and set(r4.variations) == {"6:5:C>A", "10:6:G>A", "11:0:ins(G)"}
+    motifs = {r.motif for r in by["test6_NESTED_long20_short4"]}
+    assert "TGCTGATCGTAGCTAGCTGA" in motifs and "TGCT" in motifs and "CTGA" not in motifs
+    assert len(by["test12_LONG_IMPERFECT_indel"]) == 1
+    r12 = by["test12_LONG_IMPERFECT_indel"][0]
+    assert r12.variations and any(v.startswith("9:10:del(") for v in r12.variations)

@@ -145,3 +145,14 @@ def test_period_scan_rows(detect, oracle, n, seed):
     want, wit = oracle.period_scan(text, allow_mismatches=False, tier1_mask=mask, min_period=2, max_period=60)
     got, git = detect.period_scan_rows(text, allow_mismatches=False, tier1_mask=mask, min_period=2, max_period=60)
     assert git == wit and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("params", [(20, 120, 2, 3), (2, 40, 1, 4), (3, 60, 3, 3)])
+def test_strict_rows_with_mismatches(detect, oracle, params):
+    # Hamming-tolerant adjacency (the API default max_mismatch=2), greedy-replay engine
+    s = gen_contig(9000, 31, sub_rate=0.05)
+    text = s.tobytes() + b"ACGTTGCAATGGCCATTGCA" * 12 + b"ACGTTGCAATGGCCATTGCT" * 3 + b"$"
+    want = oracle.strict_scan(text, *params)
+    got = detect.strict_rows(text, *params)
+    assert np.array_equal(got, want), f"{len(got)} vs {len(want)}"
+    assert len(want) > 0
