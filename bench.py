@@ -128,25 +128,18 @@ class IndexStep:
         self.nrows = 5
         self.ncp = n // 128 + 1 + (1 if n % 128 else 0)
         self.occ = torch.zeros((self.nrows, self.ncp), dtype=torch.int32, device=device)
-        self.ws_sa = torch.empty(int(L.bwtk_sa_workspace_bytes(n)), dtype=torch.uint8, device=device)
-        self.ws_lcp = torch.empty(int(L.bwtk_lcp_workspace_bytes(n)), dtype=torch.uint8, device=device)
-        self.ws_bwt = torch.empty(4096, dtype=torch.uint8, device=device)
+        self.ws = torch.empty(int(L.bwtk_index_workspace_bytes(n)), dtype=torch.uint8, device=device)
         self.totals = np.zeros(256, np.int64)
         self.stats = np.zeros(8, np.int64)
         self.row = np.full(256, -1, np.int32)
-        for r, b in enumerate(b"$ACGT"):
-            self.row[b] = r
 
     def run(self, d_text):
+        """One fused call: C array + SA (+ISA) + BWT + Occ + LCP (bwtk_index_build)."""
         L, lib, n = self.L, self.lib, self.n
-        st = lib.stream_ptr()
-        lib.check(L.bwtk_byte_histogram(d_text.data_ptr(), n, self.totals.ctypes.data, st), "hist")
-        lib.check(L.bwtk_sa_build(d_text.data_ptr(), n, self.sa.data_ptr(), self.isa.data_ptr(),
-                                  self.ws_sa.data_ptr(), self.ws_sa.numel(), self.stats.ctypes.data, st), "sa")
-        lib.check(L.bwtk_bwt_occ(d_text.data_ptr(), self.sa.data_ptr(), n, 128, self.row.ctypes.data, self.nrows,
-                                 self.bwt.data_ptr(), self.occ.data_ptr(), self.ws_bwt.data_ptr(), 4096, st), "bwt")
-        lib.check(L.bwtk_lcp_build(d_text.data_ptr(), self.sa.data_ptr(), n, self.lcp.data_ptr(),
-                                   self.ws_lcp.data_ptr(), self.ws_lcp.numel(), st), "lcp")
+        lib.check(L.bwtk_index_build(d_text.data_ptr(), n, 128, self.sa.data_ptr(), self.isa.data_ptr(),
+                                     self.bwt.data_ptr(), self.occ.data_ptr(), self.nrows, self.lcp.data_ptr(),
+                                     self.totals.ctypes.data, self.row.ctypes.data, self.stats.ctypes.data,
+                                     self.ws.data_ptr(), self.ws.numel(), lib.stream_ptr()), "index_build")
 
 
 def profile_report(L):

@@ -48,6 +48,8 @@ _SIGS = {
     "bwtk_byte_histogram": (_i32, [_p, _i64, _p, _p]),
     "bwtk_sa_workspace_bytes": (_i64, [_i64]),
     "bwtk_sa_build": (_i32, [_p, _i64, _p, _p, _p, _i64, _p, _p]),
+    "bwtk_index_workspace_bytes": (_i64, [_i64]),
+    "bwtk_index_build": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _p]),
     "bwtk_bwt_occ_workspace_bytes": (_i64, [_i64, _i32, _i32]),
     "bwtk_bwt_occ": (_i32, [_p, _p, _i64, _i32, _p, _i32, _p, _p, _p, _i64, _p]),
     "bwtk_lcp_workspace_bytes": (_i64, [_i64]),

@@ -1,4 +1,6 @@
-// index.cu -- byte histogram (C array), bit-packing, BWT + Occ checkpoints, LCP.
+// index.cu -- byte histogram (C array), bit-packing, BWT + Occ checkpoints, LCP,
+// and the fused index build that shares one histogram / one packed text between
+// the suffix array, the BWT and the LCP array.
 #include "common.cuh"
 
 #include <stdarg.h>
@@ -50,7 +52,12 @@ void end(cudaStream_t st)
 }
 }  // namespace prof
 
+int64_t sa_core_workspace_bytes(int64_t n);
+int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_t *d_sa, int32_t *d_isa_out,
+                  void *d_ws, int64_t ws_bytes, int64_t *h_stats, cudaStream_t st);
+
 // ------------------------------------------------------------------ histogram
+// out[0..255] = byte counts, out[256] = the last byte of the text
 __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restrict__ text, int64_t n,
                                                         unsigned long long *__restrict__ out)
 {
@@ -90,42 +97,57 @@ __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restric
     __syncthreads();
     unsigned int c = s_h[threadIdx.x];
     if (c) atomicAdd(&out[threadIdx.x], (unsigned long long)c);
+    if (gtid == 0 && n > 0) out[256] = text[n - 1];
 }
 
-int byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, unsigned long long *d_scratch,
+// d_scratch: 257 x u64.  Synchronises.  h_last (may be null) receives the last byte.
+int byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, int *h_last, unsigned long long *d_scratch,
                    cudaStream_t st)
 {
-    BWTK_CUDA(cudaMemsetAsync(d_scratch, 0, 256 * sizeof(unsigned long long), st));
+    BWTK_CUDA(cudaMemsetAsync(d_scratch, 0, 257 * sizeof(unsigned long long), st));
     if (n > 0) {
         int64_t want = ceil_div(n, 256 * 64);
         int grid = (int)(want < 1 ? 1 : (want > NUM_SMS * 8 ? NUM_SMS * 8 : want));
-        { prof::Scope ps("byte_hist_kernel", n, st);
-        byte_hist_kernel<<<grid, 256, 0, st>>>(d_text, n, d_scratch); }
+        {
+            prof::Scope ps("byte_hist_kernel", n, st);
+            byte_hist_kernel<<<grid, 256, 0, st>>>(d_text, n, d_scratch);
+        }
         BWTK_LAUNCH_CHECK();
     }
-    BWTK_CUDA(cudaMemcpyAsync(h_totals, d_scratch, 256 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    int64_t host[257];
+    BWTK_CUDA(cudaMemcpyAsync(host, d_scratch, 257 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     BWTK_CUDA(cudaStreamSynchronize(st));
+    memcpy(h_totals, host, 256 * sizeof(int64_t));
+    if (h_last) *h_last = (int)host[256];
     return BWTK_OK;
 }
 
 // ------------------------------------------------------------------ packing
 int64_t packed_words(int64_t n, int bits) { return ceil_div(n * bits, 32) + 4; }
 
-// one thread per output word; bits in {1,2,4,8}
-__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ text, int64_t n,
-                                                   const uint8_t *__restrict__ lut, int bits,
+struct Lut {
+    uint8_t v[256];
+};
+
+// one thread per output word; bits in {1,2,4,8}; the code table travels as a kernel parameter
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ text, int64_t n, Lut lut, int bits,
                                                    uint32_t *__restrict__ packed, int64_t nwords)
 {
     __shared__ uint8_t s_lut[256];
-    __shared__ uint8_t s_in[256 * 32];
-    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __shared__ __align__(16) uint8_t s_in[256 * 32];
+    s_lut[threadIdx.x] = lut.v[threadIdx.x];
     const int spw = 32 / bits;  // symbols per word
     const int64_t w0 = (int64_t)blockIdx.x * 256;
     const int64_t b0 = w0 * spw;
     const int tile_bytes = 256 * spw;
-    for (int i = threadIdx.x; i < tile_bytes; i += 256) {
-        int64_t g = b0 + i;
-        s_in[i] = g < n ? __ldg(text + g) : 0;
+    if ((((uintptr_t)(text + b0)) & 15) == 0 && b0 + tile_bytes <= n) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(text + b0);
+        for (int i = threadIdx.x; i < tile_bytes / 16; i += 256) reinterpret_cast<uint4 *>(s_in)[i] = __ldg(src + i);
+    } else {
+        for (int i = threadIdx.x; i < tile_bytes; i += 256) {
+            int64_t g = b0 + i;
+            s_in[i] = g < n ? __ldg(text + g) : 0;
+        }
     }
     __syncthreads();
     int64_t w = w0 + threadIdx.x;
@@ -140,58 +162,60 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ t
     packed[w] = acc;
 }
 
-int pack_text(const uint8_t *d_text, int64_t n, const uint8_t *h_lut, int bits, uint32_t *d_packed,
-              uint8_t *d_lut_scratch, cudaStream_t st)
-{
-    BWTK_CUDA(cudaMemcpyAsync(d_lut_scratch, h_lut, 256, cudaMemcpyHostToDevice, st));
-    int64_t nwords = packed_words(n, bits);
-    { prof::Scope ps("pack_kernel", n + nwords * 4, st);
-    pack_kernel<<<(unsigned)ceil_div(nwords, 256), 256, 0, st>>>(d_text, n, d_lut_scratch, bits,
-                                                                 d_packed, nwords); }
-    BWTK_LAUNCH_CHECK();
-    // the LUT came from the caller's stack: make sure the copy has been consumed
-    BWTK_CUDA(cudaStreamSynchronize(st));
-    return BWTK_OK;
-}
-
 // Chooses the packing of a text: returns bits, fills lut; *fast = ACGT$ layout
-// ('$' shares code 0 with 'A').
-int choose_packing(const uint8_t *d_text, int64_t n, const int64_t *totals, uint8_t *lut, bool *fast,
-                   cudaStream_t st)
+// ('$', the unique last symbol, shares code 0 with 'A').
+static int choose_packing(int64_t n, const int64_t *totals, int last_byte, Lut *lut, bool *fast)
 {
-    memset(lut, 0, 256);
+    memset(lut->v, 0, 256);
     int sigma = 0;
     for (int b = 0; b < 256; b++) sigma += totals[b] > 0;
     int64_t acgt = totals['A'] + totals['C'] + totals['G'] + totals['T'];
-    *fast = (n > 0 && totals['$'] == 1 && acgt == n - 1);
+    *fast = (n > 0 && totals['$'] == 1 && acgt == n - 1 && last_byte == '$');
     if (*fast) {
-        uint8_t last = 0;
-        if (cudaMemcpyAsync(&last, d_text + n - 1, 1, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess)
-            return -1;
-        *fast = (last == '$');
-    }
-    if (*fast) {
-        lut['A'] = 0; lut['C'] = 1; lut['G'] = 2; lut['T'] = 3; lut['$'] = 0;
+        lut->v['A'] = 0; lut->v['C'] = 1; lut->v['G'] = 2; lut->v['T'] = 3; lut->v['$'] = 0;
         return 2;
     }
     int d = 0;
     for (int b = 0; b < 256; b++)
-        if (totals[b] > 0) lut[b] = (uint8_t)d++;
+        if (totals[b] > 0) lut->v[b] = (uint8_t)d++;
     return sigma <= 2 ? 1 : sigma <= 4 ? 2 : sigma <= 16 ? 4 : 8;
 }
 
+// Histogram (one host sync) + packing of the text.  d_packed needs packed_words(n, 8)
+// words, d_hist_scratch 257 x u64.
+int prepare_text(const uint8_t *d_text, int64_t n, uint32_t *d_packed, unsigned long long *d_hist_scratch,
+                 int64_t *h_totals, int *bits_out, bool *fast_out, cudaStream_t st)
+{
+    int last = 0;
+    int rc = byte_histogram(d_text, n, h_totals, &last, d_hist_scratch, st);
+    if (rc) return rc;
+    Lut lut;
+    int bits = choose_packing(n, h_totals, last, &lut, fast_out);
+    *bits_out = bits;
+    int64_t nwords = packed_words(n, bits);
+    {
+        prof::Scope ps("pack_kernel", n + nwords * 4, st);
+        pack_kernel<<<(unsigned)ceil_div(nwords, 256), 256, 0, st>>>(d_text, n, lut, bits, d_packed, nwords);
+    }
+    BWTK_LAUNCH_CHECK();
+    return BWTK_OK;
+}
+
 // ------------------------------------------------------------------ BWT + Occ
+struct RowMap {
+    int16_t row[256];  // row of each byte value in the Occ matrix, -1 if absent
+};
+
 // One warp per checkpoint block: gathers the block's BWT bytes, stores them, and
 // writes the block's per-row symbol counts into occ[row][blk+1] (prefix-summed
 // later, in place).
 __global__ void __launch_bounds__(256)
-    bwt_block_kernel(const uint8_t *__restrict__ text, const int32_t *__restrict__ sa, int64_t n,
-                     int occ_rate, const int32_t *__restrict__ row_of_code, int nrows,
-                     uint8_t *__restrict__ bwt, int32_t *__restrict__ occ, int64_t ncp, int64_t nblk)
+    bwt_block_kernel(const uint8_t *__restrict__ text, const int32_t *__restrict__ sa, int64_t n, int occ_rate,
+                     RowMap rows, int nrows, uint8_t *__restrict__ bwt, int32_t *__restrict__ occ, int64_t ncp,
+                     int64_t nblk)
 {
     __shared__ int s_row[256];
-    s_row[threadIdx.x] = row_of_code[threadIdx.x];
+    s_row[threadIdx.x] = rows.row[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -238,7 +262,7 @@ __global__ void __launch_bounds__(1024) occ_scan_kernel(int32_t *__restrict__ oc
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { row[0] = 0; s_carry = 0; }
     __syncthreads();
-    constexpr int IT = 4;
+    constexpr int IT = 16;
     for (int64_t base = 0; base < nblk; base += 1024 * IT) {
         int v[IT], sum = 0;
 #pragma unroll
@@ -280,6 +304,26 @@ __global__ void __launch_bounds__(1024) occ_scan_kernel(int32_t *__restrict__ oc
     }
 }
 
+static int launch_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int occ_rate, const RowMap &rows,
+                          int nrows, uint8_t *d_bwt, int32_t *d_occ, cudaStream_t st)
+{
+    int64_t nblk = ceil_div(n, occ_rate);
+    int64_t ncp = n / occ_rate + 1 + (n % occ_rate != 0);
+    int64_t grid = ceil_div(nblk, 8);
+    if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
+    {
+        prof::Scope ps("bwt_block_kernel", n * 5 + (int64_t)nrows * ncp * 4, st);
+        bwt_block_kernel<<<(unsigned)grid, 256, 0, st>>>(d_text, d_sa, n, occ_rate, rows, nrows, d_bwt, d_occ, ncp, nblk);
+    }
+    BWTK_LAUNCH_CHECK();
+    {
+        prof::Scope ps("occ_scan_kernel", (int64_t)nrows * ncp * 8, st);
+        occ_scan_kernel<<<nrows, 1024, 0, st>>>(d_occ, ncp, nblk);
+    }
+    BWTK_LAUNCH_CHECK();
+    return BWTK_OK;
+}
+
 // ------------------------------------------------------------------ LCP
 // lcp[j] = LCP(suffix sa[j-1], suffix sa[j]) by direct comparison of bit-packed
 // windows (64 stream bits per step).  `slack` = 1 for the ACGT$ layout (the
@@ -306,11 +350,20 @@ __global__ void __launch_bounds__(256)
     lcp[j] = (int32_t)(h < limit ? h : limit);
 }
 
+static int launch_lcp(const uint32_t *packed, const int32_t *d_sa, int64_t n, int bits, bool fast, int32_t *d_lcp,
+                      cudaStream_t st)
+{
+    prof::Scope ps("lcp_kernel", n * 8, st);
+    lcp_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(packed, d_sa, n, bits, fast ? 1 : 0, d_lcp);
+    BWTK_LAUNCH_CHECK();
+    return BWTK_OK;
+}
+
 }  // namespace bwtk
 
 using namespace bwtk;
 
-extern "C" int32_t bwtk_version(void) { return 100; }
+extern "C" int32_t bwtk_version(void) { return 101; }
 
 extern "C" int32_t bwtk_last_error(char *buf, int32_t buflen)
 {
@@ -367,39 +420,35 @@ extern "C" int32_t bwtk_byte_histogram(const uint8_t *d_text, int64_t n, int64_t
     BWTK_REQUIRE(h_totals && n >= 0, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *scratch = nullptr;
-    BWTK_CUDA(cudaMallocAsync((void **)&scratch, 256 * sizeof(unsigned long long), st));
-    int rc = byte_histogram(d_text, n, h_totals, scratch, st);
+    BWTK_CUDA(cudaMallocAsync((void **)&scratch, 257 * sizeof(unsigned long long), st));
+    int rc = byte_histogram(d_text, n, h_totals, nullptr, scratch, st);
     cudaFreeAsync(scratch, st);
     return rc;
 }
 
-extern "C" int64_t bwtk_bwt_occ_workspace_bytes(int64_t, int32_t, int32_t) { return 4096; }
+static int make_rowmap(const int32_t *h_row_of_code, RowMap *rm)
+{
+    for (int b = 0; b < 256; b++) {
+        int r = h_row_of_code[b];
+        if (r < -1 || r > 255) return -1;
+        rm->row[b] = (int16_t)r;
+    }
+    return 0;
+}
+
+extern "C" int64_t bwtk_bwt_occ_workspace_bytes(int64_t, int32_t, int32_t) { return 256; }
 
 extern "C" int32_t bwtk_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int32_t occ_rate,
                                 const int32_t *h_row_of_code, int32_t nrows, uint8_t *d_bwt,
-                                int32_t *d_occ, void *d_ws, int64_t ws_bytes, void *stream)
+                                int32_t *d_occ, void *, int64_t, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return BWTK_OK;
-    BWTK_REQUIRE(d_text && d_sa && d_bwt && d_occ && d_ws && h_row_of_code, "null pointer");
+    BWTK_REQUIRE(d_text && d_sa && d_bwt && d_occ && h_row_of_code, "null pointer");
     BWTK_REQUIRE(occ_rate >= 1 && nrows >= 1 && nrows <= 256, "bad occ_rate/nrows");
-    BWTK_REQUIRE(ws_bytes >= 1024, "workspace too small");
-    int32_t *d_rows = (int32_t *)d_ws;
-    BWTK_CUDA(cudaMemcpyAsync(d_rows, h_row_of_code, 256 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    int64_t nblk = ceil_div(n, occ_rate);
-    int64_t ncp = n / occ_rate + 1 + (n % occ_rate != 0);
-    int64_t warps_needed = nblk;
-    int64_t grid = ceil_div(warps_needed, 8);
-    if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
-    { prof::Scope ps("bwt_block_kernel", n * 5 + (int64_t)nrows * ncp * 4, st);
-    bwt_block_kernel<<<(unsigned)grid, 256, 0, st>>>(d_text, d_sa, n, occ_rate, d_rows, nrows, d_bwt,
-                                                     d_occ, ncp, nblk); }
-    BWTK_LAUNCH_CHECK();
-    { prof::Scope ps("occ_scan_kernel", (int64_t)nrows * ncp * 8, st);
-    occ_scan_kernel<<<nrows, 1024, 0, st>>>(d_occ, ncp, nblk); }
-    BWTK_LAUNCH_CHECK();
-    BWTK_CUDA(cudaStreamSynchronize(st));  // h_row_of_code is caller memory
-    return BWTK_OK;
+    RowMap rm;
+    BWTK_REQUIRE(make_rowmap(h_row_of_code, &rm) == 0, "row_of_code entries must be in [-1, 255]");
+    return launch_bwt_occ(d_text, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, st);
 }
 
 extern "C" int64_t bwtk_lcp_workspace_bytes(int64_t n)
@@ -420,19 +469,72 @@ extern "C" int32_t bwtk_lcp_build(const uint8_t *d_text, const int32_t *d_sa, in
     }
     Carver c(d_ws, ws_bytes);
     uint32_t *packed = c.take<uint32_t>(packed_words(n, 8));
-    uint8_t *d_lut = c.take<uint8_t>(256);
-    unsigned long long *d_hist = c.take<unsigned long long>(256);
+    unsigned long long *d_hist = c.take<unsigned long long>(260);
     int64_t totals[256];
-    int rc = byte_histogram(d_text, n, totals, d_hist, st);
-    if (rc) return rc;
-    uint8_t lut[256];
+    int bits;
     bool fast;
-    int bits = choose_packing(d_text, n, totals, lut, &fast, st);
-    if (bits < 0) { set_error("choose_packing failed"); return BWTK_ECUDA; }
-    rc = pack_text(d_text, n, lut, bits, packed, d_lut, st);
+    int rc = prepare_text(d_text, n, packed, d_hist, totals, &bits, &fast, st);
     if (rc) return rc;
-    { prof::Scope ps("lcp_kernel", n * 8, st);
-    lcp_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(packed, d_sa, n, bits, fast ? 1 : 0, d_lcp); }
-    BWTK_LAUNCH_CHECK();
+    return launch_lcp(packed, d_sa, n, bits, fast, d_lcp, st);
+}
+
+// ---- fused index build: a3 + a4 + a5 + a6 + a10 with one histogram, one packed
+// text and no host round trips other than the alphabet read-back and the
+// per-batch suffix-array round counts -------------------------------------------
+extern "C" int64_t bwtk_index_workspace_bytes(int64_t n)
+{
+    if (n < 1) n = 1;
+    return sa_core_workspace_bytes(n) + align_up(packed_words(n, 8) * 4, 256) + 8192;
+}
+
+extern "C" int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t occ_rate, int32_t *d_sa,
+                                    int32_t *d_isa, uint8_t *d_bwt, int32_t *d_occ, int32_t occ_rows_cap,
+                                    int32_t *d_lcp, int64_t *h_totals, int32_t *h_row_of_code, int64_t *h_stats,
+                                    void *d_ws, int64_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h_stats) memset(h_stats, 0, 8 * sizeof(int64_t));
+    BWTK_REQUIRE(h_totals && h_row_of_code, "null host output");
+    memset(h_totals, 0, 256 * sizeof(int64_t));
+    for (int b = 0; b < 256; b++) h_row_of_code[b] = -1;
+    BWTK_REQUIRE(n >= 0 && n < (1ll << 30), "n must be in [0, 2^30)");
+    if (n == 0) return BWTK_OK;
+    BWTK_REQUIRE(d_text && d_sa && d_ws, "null pointer");
+    BWTK_REQUIRE(occ_rate >= 1, "bad occ_rate");
+    if (ws_bytes < bwtk_index_workspace_bytes(n)) {
+        set_error("index workspace: need %lld bytes, got %lld", (long long)bwtk_index_workspace_bytes(n),
+                  (long long)ws_bytes);
+        return BWTK_EWORKSPACE;
+    }
+    Carver c(d_ws, ws_bytes);
+    uint32_t *packed = c.take<uint32_t>(packed_words(n, 8));
+    unsigned long long *d_hist = c.take<unsigned long long>(260);
+    int bits;
+    bool fast;
+    int rc = prepare_text(d_text, n, packed, d_hist, h_totals, &bits, &fast, st);
+    if (rc) return rc;
+    int nrows = 0;
+    RowMap rm;
+    for (int b = 0; b < 256; b++) {
+        rm.row[b] = -1;
+        if (h_totals[b] > 0) { h_row_of_code[b] = nrows; rm.row[b] = (int16_t)nrows; nrows++; }
+    }
+    if (d_bwt && d_occ && nrows > occ_rows_cap) {
+        if (h_stats) h_stats[7] = nrows;
+        set_error("Occ matrix has room for %d rows, the text has %d distinct bytes", occ_rows_cap, nrows);
+        return BWTK_EOVERFLOW;
+    }
+    c.off = align_up(c.off, 256);
+    rc = sa_build_core(packed, n, bits, fast, d_sa, d_isa, (char *)d_ws + c.off, ws_bytes - c.off, h_stats, st);
+    if (rc) return rc;
+    if (h_stats) h_stats[7] = nrows;
+    if (d_bwt && d_occ) {
+        rc = launch_bwt_occ(d_text, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, st);
+        if (rc) return rc;
+    }
+    if (d_lcp) {
+        rc = launch_lcp(packed, d_sa, n, bits, fast, d_lcp, st);
+        if (rc) return rc;
+    }
     return BWTK_OK;
 }

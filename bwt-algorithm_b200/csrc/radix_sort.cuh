@@ -2,8 +2,11 @@
 // read + one global write per pass ("onesweep": per-tile digit offsets come from
 // a decoupled look-back over tile status words, global digit bases from one
 // up-front histogram of every pass).  Ranking inside a tile uses warp-level
-// match masks; scatters are staged through shared memory so global stores are
-// contiguous per digit.  Stable.  Keys are uint32_t or uint64_t.
+// match masks (issued four at a time for ILP) and one shared-memory atomic per
+// distinct digit per warp step; scatters are staged through shared memory so
+// global stores are contiguous per digit.  Stable.  Keys are uint32_t or
+// uint64_t.  The first pass can read its pairs from a generator (Source) instead
+// of arrays, e.g. suffix keys straight from the bit-packed text.
 #pragma once
 #include "common.cuh"
 
@@ -17,6 +20,7 @@ constexpr int WARPS = THREADS / 32;
 constexpr int ITEMS = 16;
 constexpr int TILE = THREADS * ITEMS;
 constexpr int MAX_PASSES = 8;
+constexpr int LOOKBACK_WINDOW = 4;
 static_assert(THREADS == RADIX, "one thread per digit in the look-back");
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
@@ -51,7 +55,7 @@ static inline Plan make_plan(int bit_lo, int bit_hi)
 
 struct Workspace {
     uint32_t *ghist;     // [MAX_PASSES][RADIX]
-    uint32_t *status;    // [tiles][RADIX]
+    uint32_t *status;    // [MAX_PASSES][tiles][RADIX]
     unsigned *counters;  // [MAX_PASSES] dynamic tile ids
     int *err;            // look-back spin overflow flag
     int64_t max_tiles;
@@ -60,25 +64,53 @@ struct Workspace {
 static inline int64_t tiles_for(int64_t n) { return ceil_div(n, TILE); }
 static inline int64_t workspace_bytes(int64_t n)
 {
-    return align_up(MAX_PASSES * RADIX * 4, 256) + align_up(tiles_for(n) * RADIX * 4 + 256, 256) +
-           512;
+    return align_up(MAX_PASSES * RADIX * 4, 256) +
+           align_up(MAX_PASSES * (tiles_for(n) + 1) * RADIX * 4 + 256, 256) + 512;
 }
 static inline Workspace carve(Carver &c, int64_t n)
 {
     Workspace w;
     w.ghist = c.take<uint32_t>(MAX_PASSES * RADIX);
     w.max_tiles = tiles_for(n) + 1;
-    w.status = c.take<uint32_t>(w.max_tiles * RADIX);
+    w.status = c.take<uint32_t>(MAX_PASSES * w.max_tiles * RADIX);
     w.counters = c.take<unsigned>(MAX_PASSES);
     w.err = c.take<int>(4);
     return w;
 }
 
-template <typename KeyT>
-__global__ void __launch_bounds__(512) hist_kernel(const KeyT *__restrict__ keys, int64_t n, Plan plan,
+// ---- pair sources -------------------------------------------------------------
+template <typename KeyT> struct ArraySource {
+    const KeyT *k;
+    const uint32_t *v;
+    __device__ __forceinline__ void load(int64_t t, KeyT &key, uint32_t &val) const
+    {
+        key = k[t];
+        val = v[t];
+    }
+};
+
+// Suffix keys of round 0 (sa.cu): slot t holds suffix i = n-1-t (decreasing index
+// order); key = its first S symbols, read as one window of the packed text.
+struct PackedSuffixSource {
+    const uint32_t *packed;
+    int64_t n;
+    int bits;
+    int used;  // S * bits
+    __device__ __forceinline__ void load(int64_t t, uint32_t &key, uint32_t &val) const
+    {
+        int64_t i = n - 1 - t;
+        uint32_t w = window32(packed, i * bits);
+        key = used == 32 ? w : (w >> (32 - used));
+        val = (uint32_t)i;
+    }
+};
+
+template <typename KeyT, typename Source>
+__global__ void __launch_bounds__(512) hist_kernel(Source src, int64_t n, const unsigned *__restrict__ d_n, Plan plan,
                                                    uint32_t *__restrict__ ghist)
 {
     __shared__ uint32_t s_hist[MAX_PASSES * RADIX];
+    if (d_n) n = *d_n;   // device-resident count (<= the host bound the grid was sized for)
     for (int i = threadIdx.x; i < plan.passes * RADIX; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -88,7 +120,9 @@ __global__ void __launch_bounds__(512) hist_kernel(const KeyT *__restrict__ keys
 #pragma unroll
     for (int p = 0; p < MAX_PASSES; p++) { last_d[p] = 0; run[p] = 0; }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        KeyT k = keys[i];
+        KeyT k;
+        uint32_t v;
+        src.load(i, k, v);
 #pragma unroll
         for (int p = 0; p < MAX_PASSES; p++) {
             if (p < plan.passes) {
@@ -132,13 +166,13 @@ static __global__ void scan_hist_kernel(uint32_t *ghist)
     h[threadIdx.x] = s[threadIdx.x];
 }
 
-template <typename KeyT>
-__global__ void __launch_bounds__(THREADS)
-    onesweep_kernel(const KeyT *__restrict__ kin, const uint32_t *__restrict__ vin,
-                    KeyT *__restrict__ kout, uint32_t *__restrict__ vout, int64_t n, int shift,
-                    uint32_t digit_mask, const uint32_t *__restrict__ gbase,
-                    uint32_t *status, unsigned *tile_counter, int *err)
+template <typename KeyT, typename Source, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+    onesweep_kernel(Source src, KeyT *__restrict__ kout, uint32_t *__restrict__ vout, int64_t n,
+                    const unsigned *__restrict__ d_n, int shift, uint32_t digit_mask,
+                    const uint32_t *__restrict__ gbase, uint32_t *status, unsigned *tile_counter, int *err)
 {
+    if (d_n) n = *d_n;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyT *s_keys = reinterpret_cast<KeyT *>(smem_raw);                            // TILE keys
     uint32_t *s_vals = reinterpret_cast<uint32_t *>(smem_raw + TILE * sizeof(KeyT));  // TILE values
@@ -154,31 +188,42 @@ __global__ void __launch_bounds__(THREADS)
     __syncthreads();
     const int64_t tile = s_tile;
     const int64_t base = tile * TILE;
+    if (base >= n) return;   // grid sized for an upper bound of the device-resident count
     const int tile_n = (int)((n - base) < TILE ? (n - base) : TILE);
+    const int warp_base = warp * (ITEMS * 32) + lane;
 
     KeyT key[ITEMS];
     uint32_t val[ITEMS];
     uint32_t rpos[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        int idx = warp * (ITEMS * 32) + k * 32 + lane;
-        bool valid = idx < tile_n;
-        key[k] = valid ? kin[base + idx] : (KeyT)0;
-        val[k] = valid ? vin[base + idx] : 0u;
+        int idx = warp_base + k * 32;
+        key[k] = (KeyT)0;
+        val[k] = 0u;
+        if (idx < tile_n) src.load(base + idx, key[k], val[k]);
     }
     uint32_t *my_hist = s_whist + warp * RADIX;
     const unsigned lt = lanemask_lt();
+    // rank of every key among the keys of its warp with the same digit, in index order
 #pragma unroll
-    for (int k = 0; k < ITEMS; k++) {
-        int idx = warp * (ITEMS * 32) + k * 32 + lane;
-        bool valid = idx < tile_n;
-        uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & digit_mask) : (uint32_t)RADIX;
-        unsigned m = __match_any_sync(0xffffffffu, d);
-        uint32_t prev = valid ? my_hist[d] : 0u;
-        __syncwarp();
-        if (valid && (lane == (__ffs(m) - 1))) my_hist[d] = prev + __popc(m);
-        __syncwarp();
-        rpos[k] = prev + __popc(m & lt);
+    for (int k0 = 0; k0 < ITEMS; k0 += 4) {
+        uint32_t d[4];
+        unsigned m[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bool valid = (warp_base + (k0 + j) * 32) < tile_n;
+            d[j] = valid ? ((uint32_t)(key[k0 + j] >> shift) & digit_mask) : (uint32_t)RADIX;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) m[j] = __match_any_sync(0xffffffffu, d[j]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int leader = __ffs(m[j]) - 1;
+            uint32_t before = 0;
+            if (lane == leader && d[j] < (uint32_t)RADIX) before = atomicAdd(&my_hist[d[j]], (uint32_t)__popc(m[j]));
+            before = __shfl_sync(0xffffffffu, before, leader);
+            rpos[k0 + j] = before + __popc(m[j] & lt);
+        }
     }
     __syncthreads();
 
@@ -205,7 +250,7 @@ __global__ void __launch_bounds__(THREADS)
         if (w < warp) woff += s_wsum[w];
     const uint32_t dstart = woff + incl - cnt;
 
-    // decoupled look-back for digit `tid`
+    // decoupled look-back for digit `tid`, LOOKBACK_WINDOW predecessors per round trip
     uint32_t excl = 0;
     volatile uint32_t *st = status;
     if (tile == 0) {
@@ -213,21 +258,28 @@ __global__ void __launch_bounds__(THREADS)
     } else {
         st[tile * RADIX + tid] = FLAG_AGG | cnt;
         int64_t t = tile - 1;
-        while (true) {
-            uint32_t s = st[t * RADIX + tid];
-            int spins = 0;
-            while ((s & FLAG_MASK) == 0u) {
-                if (++spins > SPIN_LIMIT) {
-                    *err = 1;
-                    s = FLAG_INCL;
-                    break;
-                }
-                __nanosleep(32);
-                s = st[t * RADIX + tid];
+        int spins = 0;
+        bool done = false;
+        while (!done) {
+            uint32_t s[LOOKBACK_WINDOW];
+#pragma unroll
+            for (int j = 0; j < LOOKBACK_WINDOW; j++)
+                s[j] = (t - j >= 0) ? (uint32_t)st[(t - j) * RADIX + tid] : (uint32_t)(2u << 30);  // before tile 0: inclusive 0
+            int used = LOOKBACK_WINDOW;
+#pragma unroll
+            for (int j = 0; j < LOOKBACK_WINDOW; j++) {
+                if (done || used != LOOKBACK_WINDOW) continue;
+                if ((s[j] & FLAG_MASK) == 0u) { used = j; continue; }   // not published yet: poll again from here
+                excl += s[j] & VAL_MASK;
+                if (s[j] & FLAG_INCL) done = true;
             }
-            excl += s & VAL_MASK;
-            if (s & FLAG_INCL) break;
-            t--;
+            if (!done) {
+                t -= used;
+                if (used != LOOKBACK_WINDOW) {
+                    if (++spins > SPIN_LIMIT) { *err = 1; done = true; }
+                    __nanosleep(20);
+                }
+            }
         }
         st[tile * RADIX + tid] = FLAG_INCL | (excl + cnt);
     }
@@ -237,7 +289,7 @@ __global__ void __launch_bounds__(THREADS)
 
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
-        int idx = warp * (ITEMS * 32) + k * 32 + lane;
+        int idx = warp_base + k * 32;
         if (idx < tile_n) {
             uint32_t d = (uint32_t)(key[k] >> shift) & digit_mask;
             uint32_t p = s_dstart[d] + my_hist[d] + rpos[k];
@@ -263,52 +315,86 @@ template <typename KeyT> constexpr size_t onesweep_smem()
 {
     return TILE * sizeof(KeyT) + TILE * 4 + WARPS * RADIX * 4 + RADIX * 4 * 2 + WARPS * 4 + 64;
 }
+template <typename KeyT> constexpr int min_blocks() { return sizeof(KeyT) == 4 ? 3 : 2; }
 
-// Sorts n pairs by key bits [bit_lo, bit_hi).  Buffers ping-pong between
-// (k0,v0) and (k1,v1); *in_first is set to 1 when the result is in (k0,v0).
-template <typename KeyT>
-int sort_pairs(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, int64_t n, int bit_lo, int bit_hi,
-               const Workspace &ws, cudaStream_t st, int *in_first, int64_t *passes_out)
+template <typename KeyT, typename Source>
+static int launch_pass(Source src, KeyT *kout, uint32_t *vout, int64_t n, const unsigned *d_n, const Plan &plan,
+                       int p, const Workspace &ws, int64_t tiles, cudaStream_t st)
 {
-    *in_first = 1;
-    if (n <= 1) return BWTK_OK;
+    auto kern = onesweep_kernel<KeyT, Source, min_blocks<KeyT>()>;
     static bool attr_set = false;
     if (!attr_set) {
-        BWTK_CUDA(cudaFuncSetAttribute(onesweep_kernel<KeyT>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)onesweep_smem<KeyT>()));
+        BWTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<KeyT>()));
         attr_set = true;
     }
+    prof::Scope ps(sizeof(KeyT) == 4 ? "onesweep_u32" : "onesweep_u64", 2 * n * (int64_t)(sizeof(KeyT) + 4), st);
+    kern<<<(unsigned)tiles, THREADS, onesweep_smem<KeyT>(), st>>>(
+        src, kout, vout, n, d_n, plan.shift[p], (1u << plan.bits[p]) - 1u, ws.ghist + p * RADIX,
+        ws.status + (int64_t)p * ws.max_tiles * RADIX, ws.counters + p, ws.err);
+    return BWTK_OK;
+}
+
+// Sorts n pairs by key bits [bit_lo, bit_hi).  The first pass reads from `first`
+// (a Source); later passes ping-pong between (k0,v0) and (k1,v1), starting by
+// writing (k0,v0) when `first` is a generator, or (k1,v1) when it wraps (k0,v0).
+// *in_first is set to 1 when the result is in (k0,v0).  When d_n is not null the
+// element count is read from device memory (n is then the bound the grids are
+// sized for) and the pass count / ping-pong parity stay those of the plan.
+template <typename KeyT, typename Source>
+int sort_pairs_from(Source first, bool first_is_k0, KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, int64_t n,
+                    int bit_lo, int bit_hi, const Workspace &ws, cudaStream_t st, int *in_first,
+                    int64_t *passes_out, const unsigned *d_n = nullptr)
+{
+    *in_first = 1;
+    if (n <= 1 && first_is_k0 && !d_n) return BWTK_OK;
+    if (n < 1) n = 1;
     Plan plan = make_plan(bit_lo, bit_hi);
     int64_t tiles = tiles_for(n);
     if (tiles > ws.max_tiles) {
-        set_error("radix sort workspace too small (%lld tiles > %lld)", (long long)tiles,
-                  (long long)ws.max_tiles);
+        set_error("radix sort workspace too small (%lld tiles > %lld)", (long long)tiles, (long long)ws.max_tiles);
         return BWTK_EWORKSPACE;
     }
     BWTK_CUDA(cudaMemsetAsync(ws.ghist, 0, MAX_PASSES * RADIX * 4, st));
     BWTK_CUDA(cudaMemsetAsync(ws.counters, 0, MAX_PASSES * sizeof(unsigned), st));
+    // status words of pass p live at ws.status + p*max_tiles*RADIX; only `tiles` of them are used
+    BWTK_CUDA(cudaMemsetAsync(ws.status, 0, (size_t)((plan.passes - 1) * ws.max_tiles + tiles) * RADIX * 4, st));
     int hgrid = (int)(ceil_div(n, 512 * 16) < NUM_SMS * 4 ? ceil_div(n, 512 * 16) : NUM_SMS * 4);
-    { prof::Scope ps(sizeof(KeyT) == 4 ? "radix_hist_u32" : "radix_hist_u64", n * (int64_t)sizeof(KeyT), st);
-    hist_kernel<KeyT><<<hgrid, 512, 0, st>>>(k0, n, plan, ws.ghist); }
+    if (hgrid < 1) hgrid = 1;
+    {
+        prof::Scope ps(sizeof(KeyT) == 4 ? "radix_hist_u32" : "radix_hist_u64", n * (int64_t)sizeof(KeyT), st);
+        hist_kernel<KeyT, Source><<<hgrid, 512, 0, st>>>(first, n, d_n, plan, ws.ghist);
+    }
     BWTK_LAUNCH_CHECK();
     scan_hist_kernel<<<plan.passes, RADIX, 0, st>>>(ws.ghist);
     BWTK_LAUNCH_CHECK();
-    KeyT *kin = k0, *kout = k1;
-    uint32_t *vin = v0, *vout = v1;
-    for (int p = 0; p < plan.passes; p++) {
-        BWTK_CUDA(cudaMemsetAsync(ws.status, 0, (size_t)tiles * RADIX * 4, st));
-        { prof::Scope ps(sizeof(KeyT) == 4 ? "onesweep_u32" : "onesweep_u64", 2 * n * (int64_t)(sizeof(KeyT) + 4), st);
-        onesweep_kernel<KeyT><<<(unsigned)tiles, THREADS, onesweep_smem<KeyT>(), st>>>(
-            kin, vin, kout, vout, n, plan.shift[p], (1u << plan.bits[p]) - 1u,
-            ws.ghist + p * RADIX, ws.status, ws.counters + p, ws.err); }
+    KeyT *kout = first_is_k0 ? k1 : k0;
+    uint32_t *vout = first_is_k0 ? v1 : v0;
+    int rc = launch_pass<KeyT, Source>(first, kout, vout, n, d_n, plan, 0, ws, tiles, st);
+    if (rc) return rc;
+    BWTK_LAUNCH_CHECK();
+    for (int p = 1; p < plan.passes; p++) {
+        ArraySource<KeyT> a{kout, vout};
+        KeyT *nk = kout == k0 ? k1 : k0;
+        uint32_t *nv = vout == v0 ? v1 : v0;
+        rc = launch_pass<KeyT, ArraySource<KeyT>>(a, nk, nv, n, d_n, plan, p, ws, tiles, st);
+        if (rc) return rc;
         BWTK_LAUNCH_CHECK();
-        KeyT *tk = kin; kin = kout; kout = tk;
-        uint32_t *tv = vin; vin = vout; vout = tv;
+        kout = nk;
+        vout = nv;
     }
-    *in_first = (kin == k0) ? 1 : 0;
+    *in_first = (kout == k0) ? 1 : 0;
     if (passes_out) *passes_out += plan.passes;
     return BWTK_OK;
+}
+
+template <typename KeyT>
+int sort_pairs(KeyT *k0, uint32_t *v0, KeyT *k1, uint32_t *v1, int64_t n, int bit_lo, int bit_hi,
+               const Workspace &ws, cudaStream_t st, int *in_first, int64_t *passes_out,
+               const unsigned *d_n = nullptr)
+{
+    ArraySource<KeyT> a{k0, v0};
+    return sort_pairs_from<KeyT, ArraySource<KeyT>>(a, true, k0, v0, k1, v1, n, bit_lo, bit_hi, ws, st, in_first,
+                                                    passes_out, d_n);
 }
 
 }  // namespace rsort

@@ -2,9 +2,10 @@
 // reference bwt.py:212-264) by prefix doubling over a bit-packed text:
 //
 //   round 0 : 32-bit key = the first S symbols of every suffix (S = 32/bits,
-//             16 bases for the ACGT$ fast path), LSD radix sort of (key, index)
-//             pairs fed in DECREASING index order, so that the stable sort puts
-//             a suffix that runs off the end of the text before longer ones
+//             16 bases for the ACGT$ fast path), read straight from the packed
+//             text by the histogram and the first radix pass; (key, index)
+//             pairs are fed in DECREASING index order, so that the stable sort
+//             puts a suffix that runs off the end of the text before longer ones
 //             with the same zero-padded key ("shorter suffix first", the
 //             reference's key2 = -1 rule);
 //   regroup : head flags -> group-head position (max-scan) -> rank[] scatter,
@@ -13,25 +14,24 @@
 //   round r : for the active suffixes only, key = (group head, rank[i+h]+1),
 //             LSD radix sort, regroup; h doubles.  Stops when nothing is active.
 //
-// The result is the unique suffix array, so it is bit-identical to the
+// The active count of every round stays in device memory: after round 0 the
+// host reads it once, then launches rounds in batches whose grids are sized for
+// the last known count (counts only shrink) and reads the count again after the
+// batch.  The result is the unique suffix array, so it is bit-identical to the
 // reference's regardless of the refinement path taken.
 #include "radix_sort.cuh"
 
 namespace bwtk {
 
-int pack_text(const uint8_t *d_text, int64_t n, const uint8_t *h_lut, int bits, uint32_t *d_packed,
-              uint8_t *d_lut_scratch, cudaStream_t st);
 int64_t packed_words(int64_t n, int bits);
-int byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, unsigned long long *d_scratch,
-                   cudaStream_t st);
-int choose_packing(const uint8_t *d_text, int64_t n, const int64_t *totals, uint8_t *lut, bool *fast,
-                   cudaStream_t st);
 
 namespace sa {
 
 constexpr int RG_THREADS = 256;
 constexpr int RG_ITEMS = 8;
 constexpr int RG_TILE = RG_THREADS * RG_ITEMS;
+constexpr int MAX_ROUNDS = 40;       // 2^40 symbols of common prefix: unreachable for n < 2^30
+constexpr int ROUND_BATCH = 4;
 
 // 64-bit look-back status: [63:62] flag, [61:31] (max head position + 1), [30:0] active count
 constexpr unsigned long long RG_AGG = 1ull << 62;
@@ -50,56 +50,60 @@ __device__ __forceinline__ unsigned long long rg_combine(unsigned long long a, u
     return rg_pack(ma > mb ? ma : mb, rg_sum(a) + rg_sum(b));
 }
 
-__global__ void init_keys_kernel(const uint32_t *__restrict__ packed, int64_t n, int bits, int S,
-                                 uint32_t *__restrict__ key, uint32_t *__restrict__ val)
-{
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    int64_t i = n - 1 - t;
-    uint32_t w = window32(packed, i * bits);
-    int used = S * bits;
-    key[t] = used == 32 ? w : (w >> (32 - used));
-    val[t] = (uint32_t)i;
-}
-
 __global__ void build_keys_kernel(const uint32_t *__restrict__ suf, const int32_t *__restrict__ grp,
-                                  const int32_t *__restrict__ rank, int64_t m, int64_t n, int64_t h,
-                                  int kbits, uint64_t *__restrict__ key)
+                                  const int32_t *__restrict__ rank, const unsigned *__restrict__ d_m, int64_t n,
+                                  int64_t h, int kbits, uint64_t *__restrict__ key)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
+    if (t >= (int64_t)*d_m) return;
     int64_t s = (int64_t)suf[t] + h;
     uint64_t k2 = s < n ? (uint64_t)(__ldg(rank + s) + 1) : 0ull;
     key[t] = ((uint64_t)(uint32_t)grp[t] << kbits) | k2;
 }
 
-// One pass over the sorted (key, suffix) list: see file header.
+// One pass over the sorted (key, suffix) list: see file header.  The element
+// count is m_host when d_m is null, else *d_m (grid sized for an upper bound).
 template <typename KeyT, bool FIRST>
 __global__ void __launch_bounds__(RG_THREADS)
     regroup_kernel(const KeyT *__restrict__ skey, const uint32_t *__restrict__ ssuf,
-                   const int32_t *__restrict__ pos, int64_t m, int64_t short_from,
-                   int32_t *__restrict__ sa, int32_t *__restrict__ rank,
+                   const int32_t *__restrict__ pos, int64_t m, const unsigned *__restrict__ d_m,
+                   int64_t short_from, int32_t *__restrict__ sa, int32_t *__restrict__ rank,
                    int32_t *__restrict__ npos, uint32_t *__restrict__ nsuf, int32_t *__restrict__ ngrp,
                    unsigned long long *status, unsigned *tile_counter, unsigned *out_count, int *err)
 {
     __shared__ unsigned s_tile;
     __shared__ unsigned long long s_warp[RG_THREADS / 32];
     __shared__ unsigned long long s_prefix;
+    // Tile elements tile0-1 .. tile0+TILE are staged through shared memory (coalesced
+    // global loads, blocked reads); one pad slot per 8 elements keeps the stride-8
+    // blocked reads conflict-free.
+    __shared__ KeyT s_key[RG_TILE + 2 + (RG_TILE + 2) / 8 + 1];
+    __shared__ uint32_t s_suf[RG_TILE + 2 + (RG_TILE + 2) / 8 + 1];
+    if (d_m) m = *d_m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     __syncthreads();
     const int64_t tile = s_tile;
-    const int64_t t0 = tile * RG_TILE + (int64_t)tid * RG_ITEMS;
+    const int64_t tile0 = tile * RG_TILE;
+    if (tile0 >= m) return;
+    const int64_t t0 = tile0 + (int64_t)tid * RG_ITEMS;
 
-    // keys/suffixes t0-1 .. t0+ITEMS (heads need the predecessor, activity the successor)
+    for (int e = tid; e < RG_TILE + 2; e += RG_THREADS) {
+        int64_t t = tile0 - 1 + e;
+        bool ok = t >= 0 && t < m;
+        s_key[e + (e >> 3)] = ok ? skey[t] : (KeyT)0;
+        uint32_t sv = ok ? ssuf[t] : 0u;
+        s_suf[e + (e >> 3)] = sv;
+        if (FIRST && ok && e >= 1 && e <= RG_TILE) sa[t] = (int32_t)sv;   // SA[t] = sorted suffix, coalesced
+    }
+    __syncthreads();
     KeyT k[RG_ITEMS + 2];
     uint32_t sf[RG_ITEMS + 2];
 #pragma unroll
     for (int j = 0; j < RG_ITEMS + 2; j++) {
-        int64_t t = t0 - 1 + j;
-        bool ok = t >= 0 && t < m;
-        k[j] = ok ? skey[t] : (KeyT)0;
-        sf[j] = ok ? ssuf[t] : 0u;
+        int e = tid * RG_ITEMS + j;
+        k[j] = s_key[e + (e >> 3)];
+        sf[j] = s_suf[e + (e >> 3)];
     }
     bool head[RG_ITEMS + 1];
 #pragma unroll
@@ -122,8 +126,7 @@ __global__ void __launch_bounds__(RG_THREADS)
             if (!(head[j] && head[j + 1])) lsum++;
         }
     }
-    unsigned long long agg = rg_pack(lmax, lsum);
-    unsigned long long inc = agg;
+    unsigned long long inc = rg_pack(lmax, lsum);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -147,21 +150,28 @@ __global__ void __launch_bounds__(RG_THREADS)
         } else {
             st[tile] = RG_AGG | tile_agg;
             int64_t t = tile - 1;
-            while (true) {
-                unsigned long long s = st[t];
-                int spins = 0;
-                while ((s & RG_FLAGS) == 0ull) {
-                    if (++spins > rsort::SPIN_LIMIT) {
-                        *err = 2;
-                        s = RG_INCL;
-                        break;
-                    }
-                    __nanosleep(32);
-                    s = st[t];
+            int spins = 0;
+            bool done = false;
+            constexpr int W = 8;   // predecessors polled per round trip
+            while (!done) {
+                unsigned long long s[W];
+#pragma unroll
+                for (int j = 0; j < W; j++) s[j] = (t - j >= 0) ? (unsigned long long)st[t - j] : (2ull << 62);
+                int used = W;
+#pragma unroll
+                for (int j = 0; j < W; j++) {
+                    if (done || used != W) continue;
+                    if ((s[j] & RG_FLAGS) == 0ull) { used = j; continue; }
+                    excl = rg_combine(s[j] & ~RG_FLAGS, excl);
+                    if (s[j] & RG_INCL) done = true;
                 }
-                excl = rg_combine(s & ~RG_FLAGS, excl);
-                if (s & RG_INCL) break;
-                t--;
+                if (!done) {
+                    t -= used;
+                    if (used != W) {
+                        if (++spins > rsort::SPIN_LIMIT) { *err = 2; done = true; }
+                        __nanosleep(20);
+                    }
+                }
             }
             st[tile] = RG_INCL | rg_combine(excl, tile_agg);
         }
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(RG_THREADS)
             if (head[j]) cur_max = (uint32_t)p[j] + 1u;
             int32_t hp = (int32_t)cur_max - 1;
             uint32_t s = sf[j + 1];
-            sa[p[j]] = (int32_t)s;
+            if (!FIRST) sa[p[j]] = (int32_t)s;   // round 0 wrote SA from the staged tile
             rank[s] = hp;
             if (!(head[j] && head[j + 1])) {
                 npos[cur_sum] = p[j];
@@ -198,24 +208,176 @@ static int bits_for(int64_t v)  // bits needed to represent values 0..v
 }
 
 }  // namespace sa
-}  // namespace bwtk
 
-using namespace bwtk;
-
-extern "C" int64_t bwtk_sa_workspace_bytes(int64_t n)
+// Workspace of the doubling rounds (the packed text is provided by the caller).
+int64_t sa_core_workspace_bytes(int64_t n)
 {
     if (n < 1) n = 1;
     int64_t b = 0;
-    b += align_up(n * 4, 256);                        // rank
+    b += align_up(n * 4, 256);                        // rank (unless the caller passes an ISA buffer)
     b += 2 * align_up(n * 8, 256);                    // key buffers A, B
     b += 2 * align_up(n * 4, 256);                    // value buffers
     b += 2 * align_up(n * 4, 256);                    // position buffers
     b += align_up(n * 4, 256);                        // group heads
-    b += align_up(packed_words(n, 8) * 4, 256);       // packed text (worst case 8 bits)
     b += align_up(ceil_div(n, sa::RG_TILE) * 8 + 256, 256);  // regroup status
     b += rsort::workspace_bytes(n);
-    b += 4096;                                        // counters, lut, histogram scratch
+    b += 8192;                                        // counters
     return b;
+}
+
+// Suffix array of the text whose packed form (bits per symbol, `fast` = ACGT$
+// layout) is already on the device.  Synchronises the stream.
+int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_t *d_sa, int32_t *d_isa_out,
+                  void *d_ws, int64_t ws_bytes, int64_t *h_stats, cudaStream_t st)
+{
+    if (h_stats) memset(h_stats, 0, 8 * sizeof(int64_t));
+    if (ws_bytes < sa_core_workspace_bytes(n)) {
+        set_error("sa workspace: need %lld bytes, got %lld", (long long)sa_core_workspace_bytes(n),
+                  (long long)ws_bytes);
+        return BWTK_EWORKSPACE;
+    }
+    if (n == 1) {
+        BWTK_CUDA(cudaMemsetAsync(d_sa, 0, 4, st));
+        if (d_isa_out) BWTK_CUDA(cudaMemsetAsync(d_isa_out, 0, 4, st));
+        BWTK_CUDA(cudaStreamSynchronize(st));
+        if (h_stats) { h_stats[0] = 1; h_stats[1] = bits; h_stats[2] = 32 / bits; h_stats[6] = fast ? 1 : 0; }
+        return BWTK_OK;
+    }
+    Carver c(d_ws, ws_bytes);
+    int32_t *rank = c.take<int32_t>(n);
+    uint64_t *keyA = c.take<uint64_t>(n);
+    uint64_t *keyB = c.take<uint64_t>(n);
+    uint32_t *val0 = c.take<uint32_t>(n);
+    uint32_t *val1 = c.take<uint32_t>(n);
+    int32_t *pos0 = c.take<int32_t>(n);
+    int32_t *pos1 = c.take<int32_t>(n);
+    int32_t *grp = c.take<int32_t>(n);
+    int64_t rg_tiles_max = ceil_div(n, sa::RG_TILE);
+    unsigned long long *rg_status = c.take<unsigned long long>(rg_tiles_max + 8);
+    rsort::Workspace rws = rsort::carve(c, n);
+    unsigned *counters = c.take<unsigned>(sa::MAX_ROUNDS + 8);  // [0] regroup tile id, [1+r] active count entering round r
+    if (!c.ok()) {
+        set_error("sa workspace carve overflow");
+        return BWTK_EWORKSPACE;
+    }
+    if (d_isa_out) rank = d_isa_out;
+    unsigned *d_counts = counters + 1;
+    const int S = 32 / bits;
+
+    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
+    BWTK_CUDA(cudaMemsetAsync(counters, 0, (sa::MAX_ROUNDS + 8) * sizeof(unsigned), st));
+    int64_t passes = 0;
+    int in_first = 1;
+    uint32_t *key32a = (uint32_t *)keyA, *key32b = (uint32_t *)keyA + n;
+    {
+        // round 0: the histogram and the first radix pass read the suffix keys
+        // straight from the packed text (no key/value arrays are materialised)
+        rsort::PackedSuffixSource src{packed, n, bits, S * bits};
+        int rc = rsort::sort_pairs_from<uint32_t, rsort::PackedSuffixSource>(src, false, key32a, val0, key32b, val1, n,
+                                                                            0, S * bits, rws, st, &in_first, &passes);
+        if (rc) return rc;
+    }
+    uint32_t *skey32 = in_first ? key32a : key32b;
+    uint32_t *sval = in_first ? val0 : val1;
+    int32_t *pos_in = pos0, *pos_out = pos1;
+    uint32_t *suf_other = in_first ? val1 : val0;  // free value buffer receives the active suffixes
+    {
+        int64_t tiles = ceil_div(n, sa::RG_TILE);
+        BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
+        {
+            prof::Scope ps("regroup_first", n * 16, st);
+            sa::regroup_kernel<uint32_t, true><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
+                skey32, sval, nullptr, n, nullptr, n - S + 1, d_sa, rank, pos_out, suf_other, grp, rg_status, counters,
+                d_counts + 1, rws.err);
+        }
+        BWTK_LAUNCH_CHECK();
+    }
+    unsigned h_count = 0;
+    BWTK_CUDA(cudaMemcpyAsync(&h_count, d_counts + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    const int64_t active0 = h_count;
+    // after round 0 the active list lives in (pos_out, suf_other, grp)
+    uint32_t *suf_in = suf_other;
+    uint32_t *suf_free = sval;
+    { int32_t *t = pos_in; pos_in = pos_out; pos_out = t; }
+    const int kbits = sa::bits_for(n);
+    const int gbits = sa::bits_for(n - 1);
+    int64_t h = S;
+    int round = 1;   // next round index; its count is d_counts[round]
+    while (h_count > 0) {
+        const int64_t bound = h_count;   // counts only shrink
+        int launched = 0;
+        for (; launched < sa::ROUND_BATCH && round < sa::MAX_ROUNDS; launched++, round++) {
+            const unsigned *d_m = d_counts + round;
+            {
+                prof::Scope ps("build_keys_kernel", bound * 20, st);
+                sa::build_keys_kernel<<<(unsigned)ceil_div(bound, 256), 256, 0, st>>>(suf_in, grp, rank, d_m, n, h, kbits,
+                                                                                     keyA);
+            }
+            BWTK_LAUNCH_CHECK();
+            int rc = rsort::sort_pairs<uint64_t>(keyA, suf_in, keyB, suf_free, bound, 0, kbits + gbits, rws, st,
+                                                 &in_first, &passes, d_m);
+            if (rc) return rc;
+            uint64_t *sk = in_first ? keyA : keyB;
+            uint32_t *ss = in_first ? suf_in : suf_free;
+            uint32_t *sn = in_first ? suf_free : suf_in;  // the other value buffer takes the next list
+            int64_t tiles = ceil_div(bound, sa::RG_TILE);
+            BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
+            BWTK_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned), st));
+            {
+                prof::Scope ps("regroup_round", bound * 36, st);
+                sa::regroup_kernel<uint64_t, false><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
+                    sk, ss, pos_in, bound, d_m, 0, d_sa, rank, pos_out, sn, grp, rg_status, counters,
+                    d_counts + round + 1, rws.err);
+            }
+            BWTK_LAUNCH_CHECK();
+            suf_in = sn;
+            suf_free = ss;
+            { int32_t *t = pos_in; pos_in = pos_out; pos_out = t; }
+            h <<= 1;
+        }
+        BWTK_CUDA(cudaMemcpyAsync(&h_count, d_counts + round, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        BWTK_CUDA(cudaStreamSynchronize(st));
+        if (h_count > 0 && (round >= sa::MAX_ROUNDS || h > 4 * n)) {
+            set_error("suffix array refinement did not converge");
+            return BWTK_EINTERNAL;
+        }
+    }
+    int h_err = 0;
+    unsigned h_counts[sa::MAX_ROUNDS + 1];
+    BWTK_CUDA(cudaMemcpyAsync(&h_err, rws.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    if (h_err) {
+        set_error("look-back spin limit hit (code %d)", h_err);
+        return BWTK_EINTERNAL;
+    }
+    if (h_stats) {
+        int64_t sum_active = 0, rounds = 1;
+        for (int r = 1; r < sa::MAX_ROUNDS; r++) {
+            if (h_counts[r] == 0) break;
+            sum_active += h_counts[r];
+            rounds++;
+        }
+        h_stats[0] = rounds; h_stats[1] = bits; h_stats[2] = S; h_stats[3] = active0;
+        h_stats[4] = sum_active; h_stats[5] = passes; h_stats[6] = fast ? 1 : 0;
+    }
+    return BWTK_OK;
+}
+
+}  // namespace bwtk
+
+using namespace bwtk;
+
+namespace bwtk {
+int prepare_text(const uint8_t *d_text, int64_t n, uint32_t *d_packed, unsigned long long *d_hist_scratch,
+                 int64_t *h_totals, int *bits_out, bool *fast_out, cudaStream_t st);
+}
+
+extern "C" int64_t bwtk_sa_workspace_bytes(int64_t n)
+{
+    if (n < 1) n = 1;
+    return sa_core_workspace_bytes(n) + align_up(packed_words(n, 8) * 4, 256) + 4096;
 }
 
 extern "C" int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa, int32_t *d_isa_out,
@@ -232,132 +394,13 @@ extern "C" int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa
         return BWTK_EWORKSPACE;
     }
     Carver c(d_ws, ws_bytes);
-    int32_t *rank = c.take<int32_t>(n);
-    uint64_t *keyA = c.take<uint64_t>(n);
-    uint64_t *keyB = c.take<uint64_t>(n);
-    uint32_t *val0 = c.take<uint32_t>(n);
-    uint32_t *val1 = c.take<uint32_t>(n);
-    int32_t *pos0 = c.take<int32_t>(n);
-    int32_t *pos1 = c.take<int32_t>(n);
-    int32_t *grp = c.take<int32_t>(n);
     uint32_t *packed = c.take<uint32_t>(packed_words(n, 8));
-    int64_t rg_tiles_max = ceil_div(n, sa::RG_TILE);
-    unsigned long long *rg_status = c.take<unsigned long long>(rg_tiles_max + 8);
-    rsort::Workspace rws = rsort::carve(c, n);
-    unsigned *counters = c.take<unsigned>(16);  // [0] regroup tile counter, [1] active count
-    uint8_t *d_lut = c.take<uint8_t>(256);
-    unsigned long long *d_hist = c.take<unsigned long long>(256);
-    if (!c.ok()) {
-        set_error("sa workspace carve overflow");
-        return BWTK_EWORKSPACE;
-    }
-    if (d_isa_out) rank = d_isa_out;
-
-    // alphabet -> bits per symbol
+    unsigned long long *d_hist = c.take<unsigned long long>(260);
     int64_t totals[256];
-    int rc = byte_histogram(d_text, n, totals, d_hist, st);
-    if (rc) return rc;
-    uint8_t lut[256];
+    int bits;
     bool fast;
-    // ACGT$ layout: '$' shares code 0 with 'A'; it is the unique last symbol, so
-    // every suffix whose first S symbols reach past it is made a singleton in
-    // round 0, and the one ending exactly on it is ordered by the past-the-end
-    // key (0) in round 1.
-    int bits = choose_packing(d_text, n, totals, lut, &fast, st);
-    if (bits < 0) { set_error("choose_packing failed"); return BWTK_ECUDA; }
-    const int S = 32 / bits;
-    rc = pack_text(d_text, n, lut, bits, packed, d_lut, st);
+    int rc = prepare_text(d_text, n, packed, d_hist, totals, &bits, &fast, st);
     if (rc) return rc;
-
-    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
-    int64_t passes = 0, sum_active = 0, rounds = 0;
-    int in_first = 1;
-    uint32_t *key32a = (uint32_t *)keyA, *key32b = (uint32_t *)keyA + n;
-    if (n == 1) {
-        BWTK_CUDA(cudaMemsetAsync(d_sa, 0, 4, st));
-        BWTK_CUDA(cudaMemsetAsync(rank, 0, 4, st));
-        BWTK_CUDA(cudaStreamSynchronize(st));
-        return BWTK_OK;
-    }
-    {
-        int thr = 256;
-        { prof::Scope ps("init_keys_kernel", n * 8 + n * bits / 8, st);
-        sa::init_keys_kernel<<<(unsigned)ceil_div(n, thr), thr, 0, st>>>(packed, n, bits, S, key32a, val0); }
-        BWTK_LAUNCH_CHECK();
-        rc = rsort::sort_pairs<uint32_t>(key32a, val0, key32b, val1, n, 0, S * bits, rws, st, &in_first,
-                                         &passes);
-        if (rc) return rc;
-    }
-    uint32_t *skey32 = in_first ? key32a : key32b;
-    uint32_t *sval = in_first ? val0 : val1;
-    int32_t *pos_in = pos0, *pos_out = pos1;
-    uint32_t *suf_other = in_first ? val1 : val0;  // free value buffer receives the active suffixes
-
-    unsigned h_count = 0;
-    {
-        int64_t tiles = ceil_div(n, sa::RG_TILE);
-        BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
-        BWTK_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), st));
-        { prof::Scope ps("regroup_first", n * 16, st);
-        sa::regroup_kernel<uint32_t, true><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
-            skey32, sval, nullptr, n, n - S + 1, d_sa, rank, pos_out, suf_other, grp, rg_status,
-            counters, counters + 1, rws.err); }
-        BWTK_LAUNCH_CHECK();
-        BWTK_CUDA(cudaMemcpyAsync(&h_count, counters + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        BWTK_CUDA(cudaStreamSynchronize(st));
-    }
-    int64_t active0 = h_count;
-    rounds = 1;
-    // after round 0 the active list lives in (pos_out, suf_other, grp)
-    uint32_t *suf_in = suf_other;
-    uint32_t *suf_free = sval;
-    { int32_t *t = pos_in; pos_in = pos_out; pos_out = t; }
-    const int kbits = sa::bits_for(n);
-    const int gbits = sa::bits_for(n - 1);
-    int64_t h = S;
-    while (h_count > 0) {
-        int64_t m = h_count;
-        sum_active += m;
-        rounds++;
-        { prof::Scope ps("build_keys_kernel", m * 20, st);
-        sa::build_keys_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(suf_in, grp, rank, m, n, h,
-                                                                         kbits, keyA); }
-        BWTK_LAUNCH_CHECK();
-        rc = rsort::sort_pairs<uint64_t>(keyA, suf_in, keyB, suf_free, m, 0, kbits + gbits, rws, st,
-                                         &in_first, &passes);
-        if (rc) return rc;
-        uint64_t *sk = in_first ? keyA : keyB;
-        uint32_t *ss = in_first ? suf_in : suf_free;
-        uint32_t *sn = in_first ? suf_free : suf_in;  // the other value buffer takes the next list
-        int64_t tiles = ceil_div(m, sa::RG_TILE);
-        BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
-        BWTK_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned), st));
-        { prof::Scope ps("regroup_round", m * 36, st);
-        sa::regroup_kernel<uint64_t, false><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
-            sk, ss, pos_in, m, 0, d_sa, rank, pos_out, sn, grp, rg_status, counters, counters + 1,
-            rws.err); }
-        BWTK_LAUNCH_CHECK();
-        BWTK_CUDA(cudaMemcpyAsync(&h_count, counters + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        BWTK_CUDA(cudaStreamSynchronize(st));
-        suf_in = sn;
-        suf_free = ss;
-        { int32_t *t = pos_in; pos_in = pos_out; pos_out = t; }
-        h <<= 1;
-        if (h > 2 * n && h_count > 0) {
-            set_error("suffix array refinement did not converge");
-            return BWTK_EINTERNAL;
-        }
-    }
-    int h_err = 0;
-    BWTK_CUDA(cudaMemcpyAsync(&h_err, rws.err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaStreamSynchronize(st));
-    if (h_err) {
-        set_error("look-back spin limit hit (code %d)", h_err);
-        return BWTK_EINTERNAL;
-    }
-    if (h_stats) {
-        h_stats[0] = rounds; h_stats[1] = bits; h_stats[2] = S; h_stats[3] = active0;
-        h_stats[4] = sum_active; h_stats[5] = passes; h_stats[6] = fast ? 1 : 0;
-    }
-    return BWTK_OK;
+    c.off = align_up(c.off, 256);
+    return sa_build_core(packed, n, bits, fast, d_sa, d_isa_out, (char *)d_ws + c.off, ws_bytes - c.off, h_stats, st);
 }

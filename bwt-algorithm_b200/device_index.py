@@ -26,7 +26,7 @@ def _torch():
 
 class DeviceIndex:
     def __init__(self, text, occ_rate: int = 128, device=None, build_kmer: bool = True,
-                 text_is_device: bool = False):
+                 text_is_device: bool = False, build_lcp: bool = False):
         torch = _torch()
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -46,10 +46,32 @@ class DeviceIndex:
             n = int(self.text.numel())
             self.n = n
             st = _lib.stream_ptr()
-            # a5: C array
+            # a3 + a4 + a5 + a6 + a10 in one fused call (one histogram, one packed text)
             totals = np.zeros(256, np.int64)
+            row = np.full(256, -1, np.int32)
+            self.sa = torch.empty(n, dtype=torch.int32, device=self.device)
+            self.isa = torch.empty(n, dtype=torch.int32, device=self.device)
+            self.bwt = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self.sa_stats = np.zeros(8, np.int64)
+            self.ncp = (n // self.occ_rate + 1 + (1 if n % self.occ_rate else 0)) if n else 0
+            self._lcp = torch.empty(n, dtype=torch.int32, device=self.device) if build_lcp else None
+            rows_cap = 8
+            self.occ = torch.zeros((rows_cap, max(self.ncp, 1)), dtype=torch.int32, device=self.device)
             if n:
-                _lib.check(L.bwtk_byte_histogram(self.text.data_ptr(), n, totals.ctypes.data, st), "byte_histogram")
+                wsb = int(L.bwtk_index_workspace_bytes(n))
+                ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+                for _attempt in range(2):
+                    rc = L.bwtk_index_build(self.text.data_ptr(), n, self.occ_rate, self.sa.data_ptr(),
+                                            self.isa.data_ptr(), self.bwt.data_ptr(), self.occ.data_ptr(), rows_cap,
+                                            _lib.ptr(self._lcp), totals.ctypes.data, row.ctypes.data,
+                                            self.sa_stats.ctypes.data, ws.data_ptr(), wsb, st)
+                    if rc == _lib.E_OVERFLOW and self.sa_stats[7] > rows_cap:
+                        rows_cap = int(self.sa_stats[7])      # more than 8 distinct bytes: re-allocate Occ
+                        self.occ = torch.zeros((rows_cap, max(self.ncp, 1)), dtype=torch.int32, device=self.device)
+                        continue
+                    _lib.check(rc, "index_build")
+                    break
+                del ws
             self.totals = totals
             counts = np.zeros(256, np.int64)
             cum = 0
@@ -59,35 +81,11 @@ class DeviceIndex:
             self.counts = counts
             codes = [b for b in range(256) if totals[b] > 0]
             self.codes = codes
-            row = np.full(256, -1, np.int32)
-            for r, b in enumerate(codes):
-                row[b] = r
             self.row_of_code = row
+            self.occ = self.occ[: max(len(codes), 1)]
             self.d_C = torch.from_numpy(counts).to(self.device)
             self.d_tot = torch.from_numpy(totals).to(self.device)
             self.d_row = torch.from_numpy(row).to(self.device)
-            # a3: suffix array (+ inverse)
-            self.sa = torch.empty(n, dtype=torch.int32, device=self.device)
-            self.isa = torch.empty(n, dtype=torch.int32, device=self.device)
-            self.sa_stats = np.zeros(8, np.int64)
-            if n:
-                wsb = int(L.bwtk_sa_workspace_bytes(n))
-                ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
-                _lib.check(L.bwtk_sa_build(self.text.data_ptr(), n, self.sa.data_ptr(), self.isa.data_ptr(),
-                                           ws.data_ptr(), wsb, self.sa_stats.ctypes.data, st), "sa_build")
-                del ws
-            # a4 + a6: BWT and Occ checkpoints
-            self.ncp = (n // self.occ_rate + 1 + (1 if n % self.occ_rate else 0)) if n else 0
-            nrows = max(len(codes), 1)
-            self.bwt = torch.empty(n, dtype=torch.uint8, device=self.device)
-            self.occ = torch.zeros((nrows, max(self.ncp, 1)), dtype=torch.int32, device=self.device)
-            if n:
-                wsb = int(L.bwtk_bwt_occ_workspace_bytes(n, self.occ_rate, nrows))
-                ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
-                _lib.check(L.bwtk_bwt_occ(self.text.data_ptr(), self.sa.data_ptr(), n, self.occ_rate,
-                                          row.ctypes.data, len(codes), self.bwt.data_ptr(), self.occ.data_ptr(),
-                                          ws.data_ptr(), wsb, st), "bwt_occ")
-            self._lcp = None
             # a2: 8-mer index
             self.kmer_off = None
             self.kmer_pos = None

@@ -69,6 +69,23 @@ int64_t bwtk_sa_workspace_bytes(int64_t n);
 int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa, int32_t *d_isa_out,
                       void *d_ws, int64_t ws_bytes, int64_t *h_stats, void *stream);
 
+/* ---- a1: BWTCore.__init__ index build (bwt.py:106-136), fused ------------
+ * One call = byte histogram (a5) + suffix array (a3, + inverse) + BWT and Occ
+ * checkpoints (a4, a6) + LCP (a10), sharing one histogram and one bit-packed
+ * text.  d_isa, d_bwt/d_occ and d_lcp may be NULL to skip that output.
+ * h_totals[256] / h_row_of_code[256] (host) receive the byte counts and the Occ
+ * row of every byte value (-1 if absent; rows are in byte order).  d_occ must
+ * hold occ_rows_cap rows of ncp = n/occ_rate + 1 + (n%occ_rate != 0) int32; if
+ * the text has more distinct bytes the call returns BWTK_EOVERFLOW with the
+ * row count in h_stats[7].  h_stats as in bwtk_sa_build (+ [7] = Occ rows).
+ * Host syncs: the alphabet read-back and one per batch of doubling rounds; the
+ * BWT/Occ/LCP kernels are left in flight on the stream. */
+int64_t bwtk_index_workspace_bytes(int64_t n);
+int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t occ_rate, int32_t *d_sa, int32_t *d_isa,
+                         uint8_t *d_bwt, int32_t *d_occ, int32_t occ_rows_cap, int32_t *d_lcp,
+                         int64_t *h_totals, int32_t *h_row_of_code, int64_t *h_stats, void *d_ws,
+                         int64_t ws_bytes, void *stream);
+
 /* ---- a4+a6: _build_bwt_array + _build_occurrence_checkpoints ----------
  * (bwt.py:266-274, 288-326).  d_bwt[i] = text[(sa[i]-1) mod n].
  * h_row_of_code[256]: row index in d_occ for each byte value, -1 if the byte
