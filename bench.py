@@ -122,7 +122,6 @@ class IndexStep:
     def __init__(self, torch, L, lib, n, device):
         self.torch, self.L, self.lib, self.n, self.dev = torch, L, lib, n, device
         self.sa = torch.empty(n, dtype=torch.int32, device=device)
-        self.isa = torch.empty(n, dtype=torch.int32, device=device)
         self.bwt = torch.empty(n, dtype=torch.uint8, device=device)
         self.lcp = torch.empty(n, dtype=torch.int32, device=device)
         self.nrows = 5
@@ -136,7 +135,7 @@ class IndexStep:
     def run(self, d_text):
         """One fused call: C array + SA (+ISA) + BWT + Occ + LCP (bwtk_index_build)."""
         L, lib, n = self.L, self.lib, self.n
-        lib.check(L.bwtk_index_build(d_text.data_ptr(), n, 128, self.sa.data_ptr(), self.isa.data_ptr(),
+        lib.check(L.bwtk_index_build(d_text.data_ptr(), n, 128, self.sa.data_ptr(), None,
                                      self.bwt.data_ptr(), self.occ.data_ptr(), self.nrows, self.lcp.data_ptr(),
                                      self.totals.ctypes.data, self.row.ctypes.data, self.stats.ctypes.data,
                                      self.ws.data_ptr(), self.ws.numel(), lib.stream_ptr()), "index_build")

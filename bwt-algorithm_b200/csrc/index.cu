@@ -253,22 +253,53 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// In-place inclusive prefix sum of occ[row][1..nblk]; occ[row][0] = 0.  One block per row.
-__global__ void __launch_bounds__(1024) occ_scan_kernel(int32_t *__restrict__ occ, int64_t ncp, int64_t nblk)
+// In-place inclusive prefix sum of occ[row][1..nblk]; occ[row][0] = 0.  Each row is
+// cut into OCC_SEGS segments: segment sums first, then every segment scans itself
+// starting from the sum of the segments before it.
+constexpr int OCC_SEGS = 32;
+
+__global__ void __launch_bounds__(256) occ_partial_kernel(const int32_t *__restrict__ occ, int64_t ncp, int64_t nblk,
+                                                          int64_t seg_len, int *__restrict__ partial)
+{
+    const int seg = blockIdx.x, r = blockIdx.y;
+    const int32_t *row = occ + (int64_t)r * ncp + 1;
+    int64_t lo = (int64_t)seg * seg_len, hi = lo + seg_len < nblk ? lo + seg_len : nblk;
+    int sum = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) sum += row[i];
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ int s_w[8];
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        partial[r * OCC_SEGS + seg] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) occ_scan_kernel(int32_t *__restrict__ occ, int64_t ncp, int64_t nblk,
+                                                        int64_t seg_len, const int *__restrict__ partial)
 {
     __shared__ int s_w[32];
     __shared__ int s_carry;
-    int32_t *row = occ + (int64_t)blockIdx.x * ncp;
+    const int seg = blockIdx.x, r = blockIdx.y;
+    int32_t *row = occ + (int64_t)r * ncp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { row[0] = 0; s_carry = 0; }
+    if (tid == 0) {
+        int c = 0;
+        for (int q = 0; q < seg; q++) c += partial[r * OCC_SEGS + q];
+        s_carry = c;
+        if (seg == 0) row[0] = 0;
+    }
     __syncthreads();
-    constexpr int IT = 16;
-    for (int64_t base = 0; base < nblk; base += 1024 * IT) {
+    int64_t lo = (int64_t)seg * seg_len, hi = lo + seg_len < nblk ? lo + seg_len : nblk;
+    constexpr int IT = 4;
+    for (int64_t base = lo; base < hi; base += 1024 * IT) {
         int v[IT], sum = 0;
 #pragma unroll
         for (int k = 0; k < IT; k++) {
             int64_t i = base + (int64_t)tid * IT + k;
-            v[k] = i < nblk ? row[1 + i] : 0;
+            v[k] = i < hi ? row[1 + i] : 0;
             sum += v[k];
         }
         int inc = sum;
@@ -296,7 +327,7 @@ __global__ void __launch_bounds__(1024) occ_scan_kernel(int32_t *__restrict__ oc
         for (int k = 0; k < IT; k++) {
             int64_t i = base + (int64_t)tid * IT + k;
             run += v[k];
-            if (i < nblk) row[1 + i] = run;
+            if (i < hi) row[1 + i] = run;
         }
         __syncthreads();
         if (tid == 1023) s_carry = run;
@@ -304,8 +335,9 @@ __global__ void __launch_bounds__(1024) occ_scan_kernel(int32_t *__restrict__ oc
     }
 }
 
+// d_partial: nrows * OCC_SEGS ints of scratch
 static int launch_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int occ_rate, const RowMap &rows,
-                          int nrows, uint8_t *d_bwt, int32_t *d_occ, cudaStream_t st)
+                          int nrows, uint8_t *d_bwt, int32_t *d_occ, int *d_partial, cudaStream_t st)
 {
     int64_t nblk = ceil_div(n, occ_rate);
     int64_t ncp = n / occ_rate + 1 + (n % occ_rate != 0);
@@ -317,8 +349,12 @@ static int launch_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n,
     }
     BWTK_LAUNCH_CHECK();
     {
-        prof::Scope ps("occ_scan_kernel", (int64_t)nrows * ncp * 8, st);
-        occ_scan_kernel<<<nrows, 1024, 0, st>>>(d_occ, ncp, nblk);
+        prof::Scope ps("occ_scan_kernel", (int64_t)nrows * ncp * 12, st);
+        int64_t seg_len = ceil_div(nblk, OCC_SEGS);
+        dim3 grid(OCC_SEGS, nrows);
+        occ_partial_kernel<<<grid, 256, 0, st>>>(d_occ, ncp, nblk, seg_len, d_partial);
+        count_launch();
+        occ_scan_kernel<<<grid, 1024, 0, st>>>(d_occ, ncp, nblk, seg_len, d_partial);
     }
     BWTK_LAUNCH_CHECK();
     return BWTK_OK;
@@ -436,19 +472,23 @@ static int make_rowmap(const int32_t *h_row_of_code, RowMap *rm)
     return 0;
 }
 
-extern "C" int64_t bwtk_bwt_occ_workspace_bytes(int64_t, int32_t, int32_t) { return 256; }
+extern "C" int64_t bwtk_bwt_occ_workspace_bytes(int64_t, int32_t, int32_t nrows)
+{
+    return (int64_t)(nrows > 0 ? nrows : 1) * OCC_SEGS * 4 + 256;
+}
 
 extern "C" int32_t bwtk_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int32_t occ_rate,
                                 const int32_t *h_row_of_code, int32_t nrows, uint8_t *d_bwt,
-                                int32_t *d_occ, void *, int64_t, void *stream)
+                                int32_t *d_occ, void *d_ws, int64_t ws_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return BWTK_OK;
-    BWTK_REQUIRE(d_text && d_sa && d_bwt && d_occ && h_row_of_code, "null pointer");
+    BWTK_REQUIRE(d_text && d_sa && d_bwt && d_occ && h_row_of_code && d_ws, "null pointer");
     BWTK_REQUIRE(occ_rate >= 1 && nrows >= 1 && nrows <= 256, "bad occ_rate/nrows");
+    BWTK_REQUIRE(ws_bytes >= bwtk_bwt_occ_workspace_bytes(n, occ_rate, nrows), "workspace too small");
     RowMap rm;
     BWTK_REQUIRE(make_rowmap(h_row_of_code, &rm) == 0, "row_of_code entries must be in [-1, 255]");
-    return launch_bwt_occ(d_text, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, st);
+    return launch_bwt_occ(d_text, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, (int *)d_ws, st);
 }
 
 extern "C" int64_t bwtk_lcp_workspace_bytes(int64_t n)
@@ -484,7 +524,7 @@ extern "C" int32_t bwtk_lcp_build(const uint8_t *d_text, const int32_t *d_sa, in
 extern "C" int64_t bwtk_index_workspace_bytes(int64_t n)
 {
     if (n < 1) n = 1;
-    return sa_core_workspace_bytes(n) + align_up(packed_words(n, 8) * 4, 256) + 8192;
+    return sa_core_workspace_bytes(n) + align_up(packed_words(n, 8) * 4, 256) + 256 * OCC_SEGS * 4 + 8192;
 }
 
 extern "C" int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t occ_rate, int32_t *d_sa,
@@ -509,6 +549,7 @@ extern "C" int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t oc
     Carver c(d_ws, ws_bytes);
     uint32_t *packed = c.take<uint32_t>(packed_words(n, 8));
     unsigned long long *d_hist = c.take<unsigned long long>(260);
+    int *d_partial = c.take<int>(256 * OCC_SEGS);
     int bits;
     bool fast;
     int rc = prepare_text(d_text, n, packed, d_hist, h_totals, &bits, &fast, st);
@@ -529,7 +570,7 @@ extern "C" int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t oc
     if (rc) return rc;
     if (h_stats) h_stats[7] = nrows;
     if (d_bwt && d_occ) {
-        rc = launch_bwt_occ(d_text, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, st);
+        rc = launch_bwt_occ(d_text, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, d_partial, st);
         if (rc) return rc;
     }
     if (d_lcp) {

@@ -50,15 +50,49 @@ __device__ __forceinline__ unsigned long long rg_combine(unsigned long long a, u
     return rg_pack(ma > mb ? ma : mb, rg_sum(a) + rg_sum(b));
 }
 
-__global__ void build_keys_kernel(const uint32_t *__restrict__ suf, const int32_t *__restrict__ grp,
-                                  const int32_t *__restrict__ rank, const unsigned *__restrict__ d_m, int64_t n,
-                                  int64_t h, int kbits, uint64_t *__restrict__ key)
+// Round-0 singletons never get their rank scattered (that scatter is 46.7 M random
+// 4-byte writes for a chr21-sized contig, ~3 GB of DRAM traffic, while the doubling
+// rounds only ever read the ranks of ~10 % of the suffixes).  Their rank is their
+// SA position, recovered on demand: 16-bit prefix table -> binary search in the
+// sorted round-0 keys -> step over the (<= 15) short suffixes of that key.
+struct LazyRank {
+    const uint32_t *abits;   // bit x set: suffix x was active after round 0, rank[x] is maintained
+    const int32_t *rank;
+    const uint32_t *skey;    // round-0 keys in sorted order
+    const int32_t *ptab;     // [65537] first sorted position of every 16-bit key prefix
+    const int32_t *sa;       // singleton positions of SA never change after round 0
+    const uint32_t *packed;
+    int bits;
+    __device__ __forceinline__ int32_t operator()(int64_t x) const
+    {
+        if ((__ldg(abits + (x >> 5)) >> (x & 31)) & 1u) return __ldg(rank + x);
+        uint32_t key = window32(packed, x * bits);
+        int32_t lo = __ldg(ptab + (key >> 16)), hi = __ldg(ptab + (key >> 16) + 1);
+        while (lo < hi) {
+            int32_t mid = (lo + hi) >> 1;
+            if (__ldg(skey + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        while (__ldg(sa + lo) != (int32_t)x) lo++;
+        return lo;
+    }
+};
+
+__global__ void build_keys_kernel(const uint32_t *__restrict__ suf, const int32_t *__restrict__ grp, LazyRank lr,
+                                  const unsigned *__restrict__ d_m, int64_t n, int64_t h, int kbits,
+                                  uint64_t *__restrict__ key)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)*d_m) return;
     int64_t s = (int64_t)suf[t] + h;
-    uint64_t k2 = s < n ? (uint64_t)(__ldg(rank + s) + 1) : 0ull;
+    uint64_t k2 = s < n ? (uint64_t)(lr(s) + 1) : 0ull;
     key[t] = ((uint64_t)(uint32_t)grp[t] << kbits) | k2;
+}
+
+// isa[sa[j]] = j (only when the caller asks for the inverse suffix array)
+__global__ void invert_kernel(const int32_t *__restrict__ sa, int64_t n, int32_t *__restrict__ isa)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) isa[sa[j]] = (int32_t)j;
 }
 
 // One pass over the sorted (key, suffix) list: see file header.  The element
@@ -69,6 +103,7 @@ __global__ void __launch_bounds__(RG_THREADS)
                    const int32_t *__restrict__ pos, int64_t m, const unsigned *__restrict__ d_m,
                    int64_t short_from, int32_t *__restrict__ sa, int32_t *__restrict__ rank,
                    int32_t *__restrict__ npos, uint32_t *__restrict__ nsuf, int32_t *__restrict__ ngrp,
+                   uint32_t *__restrict__ abits, int32_t *__restrict__ ptab,
                    unsigned long long *status, unsigned *tile_counter, unsigned *out_count, int *err)
 {
     __shared__ unsigned s_tile;
@@ -189,8 +224,19 @@ __global__ void __launch_bounds__(RG_THREADS)
             int32_t hp = (int32_t)cur_max - 1;
             uint32_t s = sf[j + 1];
             if (!FIRST) sa[p[j]] = (int32_t)s;   // round 0 wrote SA from the staged tile
-            rank[s] = hp;
-            if (!(head[j] && head[j + 1])) {
+            const bool active = !(head[j] && head[j + 1]);
+            // round 0: only still-ambiguous suffixes get a rank entry (+ their bit);
+            // later rounds: every element was active once, so its entry is maintained
+            if (!FIRST || active) rank[s] = hp;
+            if (FIRST) {
+                if (active) atomicOr(abits + (s >> 5), 1u << (s & 31));
+                // first sorted position of every 16-bit key prefix
+                uint32_t pc = (uint32_t)(k[j + 1] >> 16), pp = (uint32_t)(k[j] >> 16);
+                if (t == 0) { for (uint32_t q = 0; q <= pc; q++) ptab[q] = 0; }
+                else if (pc != pp) { for (uint32_t q = pp + 1; q <= pc; q++) ptab[q] = (int32_t)t; }
+                if (t == m - 1) { for (uint32_t q = pc + 1; q <= 65536u; q++) ptab[q] = (int32_t)m; }
+            }
+            if (active) {
                 npos[cur_sum] = p[j];
                 nsuf[cur_sum] = s;
                 ngrp[cur_sum] = hp;
@@ -214,7 +260,10 @@ int64_t sa_core_workspace_bytes(int64_t n)
 {
     if (n < 1) n = 1;
     int64_t b = 0;
-    b += align_up(n * 4, 256);                        // rank (unless the caller passes an ISA buffer)
+    b += align_up(n * 4, 256);                        // rank of the suffixes that stay ambiguous after round 0
+    b += align_up(n * 4, 256);                        // round-0 keys in sorted order (lazy singleton ranks)
+    b += align_up((n / 32 + 2) * 4, 256);             // "was active" bitmap
+    b += align_up(65538 * 4, 256);                    // 16-bit key-prefix table
     b += 2 * align_up(n * 8, 256);                    // key buffers A, B
     b += 2 * align_up(n * 4, 256);                    // value buffers
     b += 2 * align_up(n * 4, 256);                    // position buffers
@@ -245,6 +294,9 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     }
     Carver c(d_ws, ws_bytes);
     int32_t *rank = c.take<int32_t>(n);
+    uint32_t *skeep = c.take<uint32_t>(n);
+    uint32_t *abits = c.take<uint32_t>(n / 32 + 2);
+    int32_t *ptab = c.take<int32_t>(65538);
     uint64_t *keyA = c.take<uint64_t>(n);
     uint64_t *keyB = c.take<uint64_t>(n);
     uint32_t *val0 = c.take<uint32_t>(n);
@@ -260,15 +312,18 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
         set_error("sa workspace carve overflow");
         return BWTK_EWORKSPACE;
     }
-    if (d_isa_out) rank = d_isa_out;
     unsigned *d_counts = counters + 1;
     const int S = 32 / bits;
 
     BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
     BWTK_CUDA(cudaMemsetAsync(counters, 0, (sa::MAX_ROUNDS + 8) * sizeof(unsigned), st));
+    BWTK_CUDA(cudaMemsetAsync(abits, 0, (size_t)(n / 32 + 2) * 4, st));
     int64_t passes = 0;
     int in_first = 1;
-    uint32_t *key32a = (uint32_t *)keyA, *key32b = (uint32_t *)keyA + n;
+    // round-0 ping-pong buffers chosen so that the sorted keys land in `skeep`
+    // (the generator pass writes k0; an odd number of passes ends in k0)
+    const bool odd = (rsort::make_plan(0, S * bits).passes & 1) != 0;
+    uint32_t *key32a = odd ? skeep : (uint32_t *)keyA, *key32b = odd ? (uint32_t *)keyA : skeep;
     {
         // round 0: the histogram and the first radix pass read the suffix keys
         // straight from the packed text (no key/value arrays are materialised)
@@ -287,8 +342,8 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
         {
             prof::Scope ps("regroup_first", n * 16, st);
             sa::regroup_kernel<uint32_t, true><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
-                skey32, sval, nullptr, n, nullptr, n - S + 1, d_sa, rank, pos_out, suf_other, grp, rg_status, counters,
-                d_counts + 1, rws.err);
+                skey32, sval, nullptr, n, nullptr, n - S + 1, d_sa, rank, pos_out, suf_other, grp, abits, ptab,
+                rg_status, counters, d_counts + 1, rws.err);
         }
         BWTK_LAUNCH_CHECK();
     }
@@ -302,6 +357,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     { int32_t *t = pos_in; pos_in = pos_out; pos_out = t; }
     const int kbits = sa::bits_for(n);
     const int gbits = sa::bits_for(n - 1);
+    const sa::LazyRank lr{abits, rank, skey32, ptab, d_sa, packed, bits};
     int64_t h = S;
     int round = 1;   // next round index; its count is d_counts[round]
     while (h_count > 0) {
@@ -311,7 +367,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
             const unsigned *d_m = d_counts + round;
             {
                 prof::Scope ps("build_keys_kernel", bound * 20, st);
-                sa::build_keys_kernel<<<(unsigned)ceil_div(bound, 256), 256, 0, st>>>(suf_in, grp, rank, d_m, n, h, kbits,
+                sa::build_keys_kernel<<<(unsigned)ceil_div(bound, 256), 256, 0, st>>>(suf_in, grp, lr, d_m, n, h, kbits,
                                                                                      keyA);
             }
             BWTK_LAUNCH_CHECK();
@@ -327,7 +383,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
             {
                 prof::Scope ps("regroup_round", bound * 36, st);
                 sa::regroup_kernel<uint64_t, false><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
-                    sk, ss, pos_in, bound, d_m, 0, d_sa, rank, pos_out, sn, grp, rg_status, counters,
+                    sk, ss, pos_in, bound, d_m, 0, d_sa, rank, pos_out, sn, grp, nullptr, nullptr, rg_status, counters,
                     d_counts + round + 1, rws.err);
             }
             BWTK_LAUNCH_CHECK();
@@ -342,6 +398,11 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
             set_error("suffix array refinement did not converge");
             return BWTK_EINTERNAL;
         }
+    }
+    if (d_isa_out) {
+        prof::Scope ps("invert_kernel", n * 8, st);
+        sa::invert_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_sa, n, d_isa_out);
+        BWTK_LAUNCH_CHECK();
     }
     int h_err = 0;
     unsigned h_counts[sa::MAX_ROUNDS + 1];

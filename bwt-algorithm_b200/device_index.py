@@ -26,7 +26,7 @@ def _torch():
 
 class DeviceIndex:
     def __init__(self, text, occ_rate: int = 128, device=None, build_kmer: bool = True,
-                 text_is_device: bool = False, build_lcp: bool = False):
+                 text_is_device: bool = False, build_lcp: bool = False, build_isa: bool = False):
         torch = _torch()
         self.torch = torch
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -50,7 +50,7 @@ class DeviceIndex:
             totals = np.zeros(256, np.int64)
             row = np.full(256, -1, np.int32)
             self.sa = torch.empty(n, dtype=torch.int32, device=self.device)
-            self.isa = torch.empty(n, dtype=torch.int32, device=self.device)
+            self.isa = torch.empty(n, dtype=torch.int32, device=self.device) if build_isa else None
             self.bwt = torch.empty(n, dtype=torch.uint8, device=self.device)
             self.sa_stats = np.zeros(8, np.int64)
             self.ncp = (n // self.occ_rate + 1 + (1 if n % self.occ_rate else 0)) if n else 0
@@ -62,7 +62,7 @@ class DeviceIndex:
                 ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
                 for _attempt in range(2):
                     rc = L.bwtk_index_build(self.text.data_ptr(), n, self.occ_rate, self.sa.data_ptr(),
-                                            self.isa.data_ptr(), self.bwt.data_ptr(), self.occ.data_ptr(), rows_cap,
+                                            _lib.ptr(self.isa), self.bwt.data_ptr(), self.occ.data_ptr(), rows_cap,
                                             _lib.ptr(self._lcp), totals.ctypes.data, row.ctypes.data,
                                             self.sa_stats.ctypes.data, ws.data_ptr(), wsb, st)
                     if rc == _lib.E_OVERFLOW and self.sa_stats[7] > rows_cap:

@@ -20,7 +20,7 @@ def DeviceIndex():
 
 
 def _check_index(DeviceIndex, oracle, text: bytes, occ_rate=128, searches=True):
-    ix = DeviceIndex(text, occ_rate=occ_rate)
+    ix = DeviceIndex(text, occ_rate=occ_rate, build_isa=True)
     oi = oracle.OracleIndex(text, occ_rate=occ_rate)
     n = len(text)
     assert ix.n == n
@@ -134,3 +134,49 @@ def test_rank_probes(DeviceIndex, oracle):
         pp = min(max(p, 0), len(text))
         want = int(np.count_nonzero(oi.bwt[:pp] == c))
         assert g == want
+
+
+def test_standalone_entry_points(oracle):
+    """bwtk_sa_build / bwtk_bwt_occ / bwtk_lcp_build / bwtk_byte_histogram called one by one
+    (the fused bwtk_index_build is what DeviceIndex uses)."""
+    import torch
+
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200 import _lib
+
+    L = _lib.lib()
+    for text in (gen_contig(70_000, 4).tobytes() + b"$", b"ACGTNNNNACGTRYACGT" * 300 + b"$", b"A" * 5000):
+        n = len(text)
+        oi = oracle.OracleIndex(text)
+        d = torch.from_numpy(np.frombuffer(text, np.uint8).copy()).cuda()
+        st = _lib.stream_ptr()
+        totals = np.zeros(256, np.int64)
+        _lib.check(L.bwtk_byte_histogram(d.data_ptr(), n, totals.ctypes.data, st), "hist")
+        assert np.array_equal(totals, oi.totals)
+        sa = torch.empty(n, dtype=torch.int32, device="cuda")
+        isa = torch.empty(n, dtype=torch.int32, device="cuda")
+        ws = torch.empty(int(L.bwtk_sa_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+        stats = np.zeros(8, np.int64)
+        _lib.check(L.bwtk_sa_build(d.data_ptr(), n, sa.data_ptr(), isa.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   stats.ctypes.data, st), "sa")
+        assert np.array_equal(sa.cpu().numpy(), oi.sa)
+        inv = np.empty(n, np.int32)
+        inv[oi.sa] = np.arange(n, dtype=np.int32)
+        assert np.array_equal(isa.cpu().numpy(), inv)
+        codes = [b for b in range(256) if totals[b] > 0]
+        row = np.full(256, -1, np.int32)
+        for r, b in enumerate(codes):
+            row[b] = r
+        ncp = n // 128 + 1 + (1 if n % 128 else 0)
+        bwt = torch.empty(n, dtype=torch.uint8, device="cuda")
+        occ = torch.zeros((len(codes), ncp), dtype=torch.int32, device="cuda")
+        ws2 = torch.empty(int(L.bwtk_bwt_occ_workspace_bytes(n, 128, len(codes))), dtype=torch.uint8, device="cuda")
+        _lib.check(L.bwtk_bwt_occ(d.data_ptr(), sa.data_ptr(), n, 128, row.ctypes.data, len(codes), bwt.data_ptr(),
+                                  occ.data_ptr(), ws2.data_ptr(), ws2.numel(), st), "bwt_occ")
+        assert np.array_equal(bwt.cpu().numpy(), oi.bwt)
+        for code, cp in oi.occ.items():
+            assert np.array_equal(occ[row[code]].cpu().numpy(), cp)
+        lcp = torch.empty(n, dtype=torch.int32, device="cuda")
+        ws3 = torch.empty(int(L.bwtk_lcp_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+        _lib.check(L.bwtk_lcp_build(d.data_ptr(), sa.data_ptr(), n, lcp.data_ptr(), ws3.data_ptr(), ws3.numel(), st), "lcp")
+        assert np.array_equal(lcp.cpu().numpy(), oi.lcp())
