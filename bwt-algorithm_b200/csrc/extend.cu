@@ -317,81 +317,218 @@ __device__ int smallest_period_buf(const uint8_t *b, int len)
 
 constexpr int64_t MAX_ITER = 100000;
 
-// One thread per period pass.  budget[pass] = visits this pass may spend
+constexpr int PASS_THREADS = 128;
+
+// Tests of one visit that need no extension state; true = the reference would
+// just step on (bwt.py:2259-2275 plus the two-copy pre-check below).
+__device__ bool visit_rejected(const ScanCfg &c, int p, int64_t i)
+{
+    const uint8_t *s = c.s;
+    if (c.mask && c.mask[i]) return true;
+    if (c.min_copies > 2) {
+        // With two copies the vote ties on every differing column, so the first right
+        // (left) extension is accepted iff the Hamming distance to the neighbouring copy
+        // is within the budget.  If neither neighbour qualifies the array stays at one
+        // copy and can never reach min_copies (>= 3).
+        const int64_t bud = (c.allow_mm && p <= 64) ? mm_budget(p, 2) : 0;
+        int64_t hr = 0, hl = bud + 1;
+        for (int q = 0; q < p && hr <= bud; q++) hr += (__ldg(s + i + q) != __ldg(s + i + p + q));
+        if (hr > bud && i - p >= 0) {
+            hl = 0;
+            for (int q = 0; q < p && hl <= bud; q++) hl += (__ldg(s + i + q) != __ldg(s + i - p + q));
+        }
+        if (hr > bud && hl > bud) return true;
+    }
+    for (int q = 0; q < p; q++) {
+        uint8_t ch = __ldg(s + i + q);
+        if (ch == 36 || ch == 78) return true;
+    }
+    return entropy_of(s, i, p, c.plogp, c.dim) < c.min_entropy;
+}
+
+// One CTA per period pass.  The reference's scan visits i, i+step, ... and only
+// jumps after an emission, and every rejecting test is free of side effects, so
+// the CTA tests PASS_THREADS consecutive visits at once; the first visit that is
+// not rejected is evaluated in full by one thread (extension, consensus, record)
+// and sets the next position.  budget[pass] = visits this pass may spend
 // (MAX_ITER in the counting run).  Rows are appended to `tmp` with
 // aux = (pass, sequence number within the pass, visit index).
-__global__ void period_pass_kernel(ScanCfg c, int64_t npass, const int64_t *__restrict__ budget,
-                                   int64_t *__restrict__ visits, int64_t *__restrict__ emits,
-                                   int32_t *__restrict__ tmp, int32_t *__restrict__ tmp_aux, int64_t tmp_cap,
-                                   unsigned long long *tmp_count, uint8_t *scratch, int maxp, int *err)
+__global__ void __launch_bounds__(PASS_THREADS)
+    period_pass_kernel(ScanCfg c, int64_t npass, const int64_t *__restrict__ budget,
+                       int64_t *__restrict__ visits, int64_t *__restrict__ emits,
+                       int32_t *__restrict__ tmp, int32_t *__restrict__ tmp_aux, int64_t tmp_cap,
+                       unsigned long long *tmp_count, uint8_t *scratch, int maxp, int *err)
 {
-    int64_t pass = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pass = blockIdx.x;
     if (pass >= npass) return;
+    __shared__ int64_t s_i, s_it, s_seq;
+    __shared__ int s_first[PASS_THREADS / 32];
+    __shared__ int s_stop;
+    constexpr int MEMO = 4;
+    __shared__ int64_t s_memo_x[MEMO], s_memo_ni[MEMO], s_memo_it[MEMO];
+    __shared__ int s_memo_emit[MEMO], s_memo_next, s_last_full;
+    __shared__ int32_t s_memo_row[MEMO][BWTK_REC_W];
+    __shared__ int64_t s_ff, s_ff_seq0, s_ff_it0, s_ff_cyc;
+    __shared__ int s_ff_hit;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = (int)(c.min_p + pass * c.per_step);
     uint8_t *my = scratch + pass * scratch_per_thread(maxp);
     Tally t = make_tally(my, maxp);
     uint8_t *cons = t.nsym + maxp;
     const uint8_t *s = c.s;
     const int64_t n = c.n;
-    int64_t allowed = budget ? budget[pass] : MAX_ITER;
-    int64_t it = 0, seq = 0;
-    int64_t i = 0;
-    while (p > 0 && i + 2 * (int64_t)p <= n) {
-        if (it >= allowed) break;
-        it++;
-        if (c.mask && c.mask[i]) { i += c.pos_step; continue; }
-        bool bad = false;
-        for (int q = 0; q < p; q++) {
-            uint8_t ch = __ldg(s + i + q);
-            if (ch == 36 || ch == 78) { bad = true; break; }
+    const int64_t allowed = budget ? budget[pass] : MAX_ITER;
+    if (tid == 0) {
+        s_i = 0; s_it = 0; s_seq = 0; s_memo_next = 0; s_last_full = -1; s_ff = 0;
+        for (int q = 0; q < MEMO; q++) { s_memo_x[q] = -1; s_memo_it[q] = -1; }
+    }
+    __syncthreads();
+    while (p > 0) {
+        const int64_t i0 = s_i, it0 = s_it;
+        if (i0 + 2 * (int64_t)p > n || it0 >= allowed) break;
+        // visit number it0 + tid at position i0 + tid*step
+        const int64_t x = i0 + (int64_t)tid * c.pos_step;
+        const bool in_range = (x + 2 * (int64_t)p <= n) && (it0 + tid < allowed);
+        const bool stop = !in_range || !visit_rejected(c, p, x);
+        unsigned bal = __ballot_sync(0xffffffffu, stop);
+        if (lane == 0) s_first[warp] = bal ? (warp * 32 + __ffs(bal) - 1) : PASS_THREADS;
+        __syncthreads();
+        if (tid == 0) {
+            int f = PASS_THREADS;
+            for (int w = 0; w < PASS_THREADS / 32; w++) f = s_first[w] < f ? s_first[w] : f;
+            s_stop = f;
         }
-        if (bad) { i += c.pos_step; continue; }
-        if (entropy_of(s, i, p, c.plogp, c.dim) < c.min_entropy) { i += c.pos_step; continue; }
-        ExtOut o = extend_with_mismatches(s, i, p, n, c.allow_mm && p <= 64, t, cons);
-        int64_t a_len = o.array_end - o.array_start;
-        if (a_len < c.min_array_len) { i += c.pos_step; continue; }
-        int64_t part = a_len - o.copies * p;
-        if (part < 0) part = 0;
-        int64_t eff = o.copies + (((double)part / (double)p) >= 0.75 ? 1 : 0);
-        if (!(o.copies >= c.min_copies || eff >= c.min_copies)) { i += c.pos_step; continue; }
-        int prim = smallest_period(s, o.full_start, p);
-        int p_eff = prim < p ? prim : p;
-        o = extend_with_mismatches(s, o.full_start, p_eff, n, c.allow_mm && p_eff <= 64, t, cons);
-        a_len = o.array_end - o.array_start;
-        part = a_len - o.copies * p_eff;
-        if (part < 0) part = 0;
-        eff = o.copies + (((double)part / (double)p_eff) >= 0.75 ? 1 : 0);
-        if (o.copies < c.min_copies && eff < c.min_copies) { i += c.pos_step; continue; }
-        int64_t tmm, mmm;
-        int64_t a_start = o.array_start, a_end = o.array_end, copies_full = o.copies, cons_start = o.full_start;
-        int64_t used = consensus(s, c.n_total, cons_start, p_eff, copies_full, t, cons, &tmm, &mmm);
-        if (!used) { i += c.pos_step; continue; }
-        int prim2 = smallest_period_buf(cons, p_eff);
-        if (prim2 < p_eff) {
-            p_eff = prim2;
-            copies_full = (a_end - a_start) / p_eff;
-            if (copies_full < 1) copies_full = 1;
-            a_end = a_start + copies_full * p_eff;
-            cons_start = a_start;
-            used = consensus(s, c.n_total, a_start, p_eff, copies_full, t, cons, &tmm, &mmm);
-            if (!used) { i += c.pos_step; continue; }
+        __syncthreads();
+        const int f = s_stop;
+        if (f == PASS_THREADS) {   // all of them step on
+            if (tid == 0) { s_i = i0 + (int64_t)PASS_THREADS * c.pos_step; s_it = it0 + PASS_THREADS; }
+            __syncthreads();
+            continue;
         }
-        if (tmp) {
-            unsigned long long slot = atomicAdd(tmp_count, 1ull);
-            if ((int64_t)slot < tmp_cap) {
-                int32_t *row = tmp + slot * BWTK_REC_W;
-                row[0] = (int32_t)a_start; row[1] = (int32_t)a_end; row[2] = p_eff; row[3] = (int32_t)copies_full;
-                row[4] = (int32_t)tmm; row[5] = (int32_t)mmm; row[6] = (int32_t)cons_start; row[7] = (int32_t)used;
-                int32_t *ax = tmp_aux + slot * 4;
-                ax[0] = (int32_t)pass; ax[1] = (int32_t)seq; ax[2] = (int32_t)it; ax[3] = 0;
+        if (tid == f) {
+            // visits 0..f-1 were rejected; this one either ends the scan or is evaluated in full
+            int64_t it = it0 + f, i = x;
+            s_ff = 0;
+            if (!in_range) {
+                s_i = i; s_it = it;   // loop condition fails on re-entry (end of text or budget)
+            } else {
+                it++;
+                // The outcome of a full evaluation is a pure function of the position, and the
+                // reference can loop (array_end <= i after the primitive-period re-extension,
+                // bwt.py:2305-2386) until the iteration cap: remember the last few outcomes.
+                int hit = -1;
+                for (int q = 0; q < MEMO; q++)
+                    if (s_memo_x[q] == i) hit = q;
+                if (hit < 0) {
+                    int64_t next_i = i + c.pos_step;
+                    int32_t row[BWTK_REC_W];
+                    bool emitted = false;
+                    do {
+                        ExtOut o = extend_with_mismatches(s, i, p, n, c.allow_mm && p <= 64, t, cons);
+                        int64_t a_len = o.array_end - o.array_start;
+                        if (a_len < c.min_array_len) break;
+                        int64_t part = a_len - o.copies * p;
+                        if (part < 0) part = 0;
+                        int64_t eff = o.copies + (((double)part / (double)p) >= 0.75 ? 1 : 0);
+                        if (!(o.copies >= c.min_copies || eff >= c.min_copies)) break;
+                        int prim = smallest_period(s, o.full_start, p);
+                        int p_eff = prim < p ? prim : p;
+                        o = extend_with_mismatches(s, o.full_start, p_eff, n, c.allow_mm && p_eff <= 64, t, cons);
+                        a_len = o.array_end - o.array_start;
+                        part = a_len - o.copies * p_eff;
+                        if (part < 0) part = 0;
+                        eff = o.copies + (((double)part / (double)p_eff) >= 0.75 ? 1 : 0);
+                        if (o.copies < c.min_copies && eff < c.min_copies) break;
+                        int64_t tmm, mmm;
+                        int64_t a_start = o.array_start, a_end = o.array_end, copies_full = o.copies,
+                                cons_start = o.full_start;
+                        int64_t used = consensus(s, c.n_total, cons_start, p_eff, copies_full, t, cons, &tmm, &mmm);
+                        if (!used) break;
+                        int prim2 = smallest_period_buf(cons, p_eff);
+                        if (prim2 < p_eff) {
+                            p_eff = prim2;
+                            copies_full = (a_end - a_start) / p_eff;
+                            if (copies_full < 1) copies_full = 1;
+                            a_end = a_start + copies_full * p_eff;
+                            cons_start = a_start;
+                            used = consensus(s, c.n_total, a_start, p_eff, copies_full, t, cons, &tmm, &mmm);
+                            if (!used) break;
+                        }
+                        row[0] = (int32_t)a_start; row[1] = (int32_t)a_end; row[2] = p_eff;
+                        row[3] = (int32_t)copies_full; row[4] = (int32_t)tmm; row[5] = (int32_t)mmm;
+                        row[6] = (int32_t)cons_start; row[7] = (int32_t)used;
+                        emitted = true;
+                        next_i = a_end;   // jump past the array (bwt.py:2386)
+                    } while (false);
+                    if (t.overflow) *err = 1;
+                    hit = s_memo_next % MEMO;
+                    s_memo_next++;
+                    s_memo_x[hit] = i;
+                    s_memo_ni[hit] = next_i;
+                    s_memo_emit[hit] = emitted ? 1 : 0;
+                    s_memo_it[hit] = -1;
+                    for (int q = 0; q < BWTK_REC_W; q++) s_memo_row[hit][q] = emitted ? row[q] : 0;
+                }
+                int64_t seq = s_seq;
+                const bool emitted = s_memo_emit[hit] != 0;
+                if (emitted) {
+                    if (tmp) {
+                        unsigned long long slot = atomicAdd(tmp_count, 1ull);
+                        if ((int64_t)slot < tmp_cap) {
+                            int32_t *row = tmp + slot * BWTK_REC_W;
+                            for (int q = 0; q < BWTK_REC_W; q++) row[q] = s_memo_row[hit][q];
+                            int32_t *ax = tmp_aux + slot * 4;
+                            ax[0] = (int32_t)pass; ax[1] = (int32_t)seq; ax[2] = (int32_t)it; ax[3] = 0;
+                        }
+                    }
+                    seq++;
+                }
+                // Simple cycle: the same position was the previous full evaluation too, so the
+                // visits in between repeat verbatim; skip whole cycles up to the budget.
+                if (s_last_full == hit && s_memo_it[hit] >= 0) {
+                    int64_t cyc = it - s_memo_it[hit];
+                    int64_t reps = cyc > 0 ? (allowed - it) / cyc : 0;
+                    if (reps > 0) {
+                        s_ff = emitted ? reps : 0;
+                        s_ff_hit = hit;
+                        s_ff_seq0 = seq;
+                        s_ff_it0 = it;
+                        s_ff_cyc = cyc;
+                        it += reps * cyc;
+                        if (emitted) seq += reps;
+                    }
+                }
+                s_memo_it[hit] = it;
+                s_last_full = hit;
+                s_seq = seq;
+                s_i = s_memo_ni[hit];
+                s_it = it;
             }
         }
-        seq++;
-        i = a_end;
+        __syncthreads();
+        if (s_ff > 0 && tmp) {
+            // duplicate rows of the skipped cycles (the host dedups them like the reference's `seen` set)
+            const int64_t reps = s_ff;
+            __shared__ unsigned long long s_ff_base;
+            if (tid == 0) s_ff_base = atomicAdd(tmp_count, (unsigned long long)reps);
+            __syncthreads();
+            for (int64_t r = tid; r < reps; r += PASS_THREADS) {
+                int64_t slot = (int64_t)s_ff_base + r;
+                if (slot < tmp_cap) {
+                    int32_t *row = tmp + slot * BWTK_REC_W;
+                    for (int q = 0; q < BWTK_REC_W; q++) row[q] = s_memo_row[s_ff_hit][q];
+                    int32_t *ax = tmp_aux + slot * 4;
+                    ax[0] = (int32_t)pass; ax[1] = (int32_t)(s_ff_seq0 + r);
+                    ax[2] = (int32_t)(s_ff_it0 + (r + 1) * s_ff_cyc); ax[3] = 0;
+                }
+            }
+            __syncthreads();
+        }
     }
-    if (t.overflow) *err = 1;
-    if (visits) visits[pass] = it;
-    if (emits) emits[pass] = seq;
+    if (tid == 0) {
+        if (visits) visits[pass] = s_it;
+        if (emits) emits[pass] = s_seq;
+    }
 }
 
 // Applies the global iteration budget: pass q may spend max(0, MAX_ITER - visits
@@ -578,15 +715,15 @@ extern "C" int32_t bwtk_period_scan(const uint8_t *d_text, int64_t n_total, int6
     int *d_err = c.take<int>(4);
     BWTK_CUDA(cudaMemsetAsync(tmp_count, 0, 16, st));
     BWTK_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
-    unsigned grid = (unsigned)ceil_div(npass, 32);
+    unsigned grid = (unsigned)npass;
     // run 1: visits per pass with an unlimited (MAX_ITER) budget each
-    ext::period_pass_kernel<<<grid, 32, 0, st>>>(cfg, npass, nullptr, visits, nullptr, nullptr, nullptr, 0,
+    ext::period_pass_kernel<<<grid, ext::PASS_THREADS, 0, st>>>(cfg, npass, nullptr, visits, nullptr, nullptr, nullptr, 0,
                                                  tmp_count, scratch, maxp, d_err);
     BWTK_LAUNCH_CHECK();
     ext::budget_kernel<<<1, 32, 0, st>>>(visits, npass, budget, d_iter);
     BWTK_LAUNCH_CHECK();
     // run 2: same walk, bounded by the global budget, rows appended
-    ext::period_pass_kernel<<<grid, 32, 0, st>>>(cfg, npass, budget, nullptr, emits, tmp, aux, tmp_cap, tmp_count,
+    ext::period_pass_kernel<<<grid, ext::PASS_THREADS, 0, st>>>(cfg, npass, budget, nullptr, emits, tmp, aux, tmp_cap, tmp_count,
                                                  scratch, maxp, d_err);
     BWTK_LAUNCH_CHECK();
     ext::offsets_kernel<<<1, 32, 0, st>>>(emits, npass, offs);

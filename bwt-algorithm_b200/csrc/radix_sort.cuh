@@ -21,7 +21,7 @@ constexpr int ITEMS = 16;
 constexpr int TILE = THREADS * ITEMS;
 constexpr int MAX_PASSES = 8;
 constexpr int LOOKBACK_WINDOW = 4;
-static_assert(THREADS == RADIX, "one thread per digit in the look-back");
+static_assert(THREADS >= RADIX && RADIX % 32 == 0, "the first RADIX threads own one digit each");
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_INCL = 2u << 30;
@@ -227,64 +227,68 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     }
     __syncthreads();
 
-    // thread d: exclusive scan over warps of digit d, tile count of digit d
-    uint32_t cnt = 0;
+    // thread d (< RADIX): exclusive scan over warps of digit d, tile count of digit d
+    uint32_t cnt = 0, incl = 0;
+    if (tid < RADIX) {
 #pragma unroll
-    for (int w = 0; w < WARPS; w++) {
-        uint32_t t = s_whist[w * RADIX + tid];
-        s_whist[w * RADIX + tid] = cnt;
-        cnt += t;
-    }
-    // exclusive scan of cnt over the 256 digits
-    uint32_t incl = cnt;
+        for (int w = 0; w < WARPS; w++) {
+            uint32_t t = s_whist[w * RADIX + tid];
+            s_whist[w * RADIX + tid] = cnt;
+            cnt += t;
+        }
+        // exclusive scan of cnt over the 256 digits
+        incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
     }
-    if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
-    uint32_t woff = 0;
+    if (tid < RADIX) {
+        uint32_t woff = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; w++)
-        if (w < warp) woff += s_wsum[w];
-    const uint32_t dstart = woff + incl - cnt;
+        for (int w = 0; w < RADIX / 32; w++)
+            if (w < warp) woff += s_wsum[w];
+        const uint32_t dstart = woff + incl - cnt;
 
-    // decoupled look-back for digit `tid`, LOOKBACK_WINDOW predecessors per round trip
-    uint32_t excl = 0;
-    volatile uint32_t *st = status;
-    if (tile == 0) {
-        st[tid] = FLAG_INCL | cnt;
-    } else {
-        st[tile * RADIX + tid] = FLAG_AGG | cnt;
-        int64_t t = tile - 1;
-        int spins = 0;
-        bool done = false;
-        while (!done) {
-            uint32_t s[LOOKBACK_WINDOW];
+        // decoupled look-back for digit `tid`, LOOKBACK_WINDOW predecessors per round trip
+        uint32_t excl = 0;
+        volatile uint32_t *st = status;
+        if (tile == 0) {
+            st[tid] = FLAG_INCL | cnt;
+        } else {
+            st[tile * RADIX + tid] = FLAG_AGG | cnt;
+            int64_t t = tile - 1;
+            int spins = 0;
+            bool done = false;
+            while (!done) {
+                uint32_t s[LOOKBACK_WINDOW];
 #pragma unroll
-            for (int j = 0; j < LOOKBACK_WINDOW; j++)
-                s[j] = (t - j >= 0) ? (uint32_t)st[(t - j) * RADIX + tid] : (uint32_t)(2u << 30);  // before tile 0: inclusive 0
-            int used = LOOKBACK_WINDOW;
+                for (int j = 0; j < LOOKBACK_WINDOW; j++)
+                    s[j] = (t - j >= 0) ? (uint32_t)st[(t - j) * RADIX + tid] : (uint32_t)(2u << 30);  // before tile 0: inclusive 0
+                int used = LOOKBACK_WINDOW;
 #pragma unroll
-            for (int j = 0; j < LOOKBACK_WINDOW; j++) {
-                if (done || used != LOOKBACK_WINDOW) continue;
-                if ((s[j] & FLAG_MASK) == 0u) { used = j; continue; }   // not published yet: poll again from here
-                excl += s[j] & VAL_MASK;
-                if (s[j] & FLAG_INCL) done = true;
-            }
-            if (!done) {
-                t -= used;
-                if (used != LOOKBACK_WINDOW) {
-                    if (++spins > SPIN_LIMIT) { *err = 1; done = true; }
-                    __nanosleep(20);
+                for (int j = 0; j < LOOKBACK_WINDOW; j++) {
+                    if (done || used != LOOKBACK_WINDOW) continue;
+                    if ((s[j] & FLAG_MASK) == 0u) { used = j; continue; }   // not published yet: poll again from here
+                    excl += s[j] & VAL_MASK;
+                    if (s[j] & FLAG_INCL) done = true;
+                }
+                if (!done) {
+                    t -= used;
+                    if (used != LOOKBACK_WINDOW) {
+                        if (++spins > SPIN_LIMIT) { *err = 1; done = true; }
+                        __nanosleep(20);
+                    }
                 }
             }
+            st[tile * RADIX + tid] = FLAG_INCL | (excl + cnt);
         }
-        st[tile * RADIX + tid] = FLAG_INCL | (excl + cnt);
+        s_dstart[tid] = dstart;
+        s_gbase[tid] = gbase[tid] + excl - dstart;
     }
-    s_dstart[tid] = dstart;
-    s_gbase[tid] = gbase[tid] + excl - dstart;
     __syncthreads();
 
 #pragma unroll
