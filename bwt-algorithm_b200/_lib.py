@@ -12,7 +12,7 @@ import subprocess
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbwtk.so")
+SO_PATH = os.environ.get("BWTK_LIB") or os.path.join(_HERE, "libbwtk.so")  # BWTK_LIB: tuning variants
 CSRC = os.path.join(_HERE, "csrc")
 
 REC_W = 8

@@ -102,6 +102,41 @@ __device__ __forceinline__ uint64_t window64(const uint32_t *__restrict__ p, int
     return ((uint64_t)hi << 32) | lo;
 }
 
+// Warp-parallel decoupled look-back over 64-bit tile status words
+// ([63:62] flag: 1 = tile aggregate, 2 = inclusive prefix; [61:0] payload).
+// All 32 lanes of one warp call it for tile > 0; 32 predecessors are inspected per
+// round trip.  `comb` must be associative and commutative with identity 0.
+// Returns the exclusive prefix of `tile`.
+template <typename Comb>
+__device__ __forceinline__ unsigned long long warp_lookback(volatile unsigned long long *st, int64_t tile, Comb comb,
+                                                            int *err, int err_code, int spin_limit)
+{
+    const unsigned long long FL = 3ull << 62, INCL = 2ull << 62;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long excl = 0;
+    int64_t t = tile - 1;
+    int spins = 0;
+    while (true) {
+        int64_t mine = t - (int64_t)lane;
+        unsigned long long s = mine >= 0 ? st[mine] : INCL;   // before tile 0: inclusive identity
+        unsigned ready = __ballot_sync(0xffffffffu, (s & FL) != 0ull);
+        unsigned incl = __ballot_sync(0xffffffffu, (s & FL) == INCL);
+        int fi = incl ? (__ffs(incl) - 1) : 32;
+        unsigned need = fi < 31 ? ((2u << fi) - 1u) : 0xffffffffu;
+        if ((ready & need) != need) {
+            if (++spins > spin_limit) { if (lane == 0) *err = err_code; return excl; }
+            __nanosleep(20);
+            continue;
+        }
+        unsigned long long v = ((need >> lane) & 1u) ? (s & ~FL) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = comb(v, __shfl_xor_sync(0xffffffffu, v, o));
+        excl = comb(excl, v);
+        if (fi < 32) return excl;
+        t -= 32;
+    }
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt()
 {

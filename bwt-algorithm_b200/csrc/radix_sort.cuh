@@ -15,12 +15,27 @@ namespace rsort {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int THREADS = 256;
+#ifndef BWTK_RS_THREADS
+#define BWTK_RS_THREADS 256
+#endif
+#ifndef BWTK_RS_ITEMS
+#define BWTK_RS_ITEMS 16
+#endif
+#ifndef BWTK_RS_WINDOW
+#define BWTK_RS_WINDOW 4
+#endif
+#ifndef BWTK_RS_MINB32
+#define BWTK_RS_MINB32 3
+#endif
+#ifndef BWTK_RS_MINB64
+#define BWTK_RS_MINB64 2
+#endif
+constexpr int THREADS = BWTK_RS_THREADS;
 constexpr int WARPS = THREADS / 32;
-constexpr int ITEMS = 16;
+constexpr int ITEMS = BWTK_RS_ITEMS;
 constexpr int TILE = THREADS * ITEMS;
 constexpr int MAX_PASSES = 8;
-constexpr int LOOKBACK_WINDOW = 4;
+constexpr int LOOKBACK_WINDOW = BWTK_RS_WINDOW;
 static_assert(THREADS >= RADIX && RADIX % 32 == 0, "the first RADIX threads own one digit each");
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
@@ -169,10 +184,11 @@ static __global__ void scan_hist_kernel(uint32_t *ghist)
 template <typename KeyT, typename Source, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     onesweep_kernel(Source src, KeyT *__restrict__ kout, uint32_t *__restrict__ vout, int64_t n,
-                    const unsigned *__restrict__ d_n, int shift, uint32_t digit_mask,
+                    const unsigned *__restrict__ d_n, int shift, int nbits,
                     const uint32_t *__restrict__ gbase, uint32_t *status, unsigned *tile_counter, int *err)
 {
     if (d_n) n = *d_n;
+    const uint32_t digit_mask = (1u << nbits) - 1u;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KeyT *s_keys = reinterpret_cast<KeyT *>(smem_raw);                            // TILE keys
     uint32_t *s_vals = reinterpret_cast<uint32_t *>(smem_raw + TILE * sizeof(KeyT));  // TILE values
@@ -214,8 +230,20 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             bool valid = (warp_base + (k0 + j) * 32) < tile_n;
             d[j] = valid ? ((uint32_t)(key[k0 + j] >> shift) & digit_mask) : (uint32_t)RADIX;
         }
+        // peer mask of equal digits from one ballot per digit bit (MATCH.ANY runs on the
+        // address-divergence unit at ~70 cycles per warp and was the kernel's bottleneck)
 #pragma unroll
-        for (int j = 0; j < 4; j++) m[j] = __match_any_sync(0xffffffffu, d[j]);
+        for (int j = 0; j < 4; j++) {
+            unsigned pm = __ballot_sync(0xffffffffu, d[j] < (uint32_t)RADIX);
+#pragma unroll
+            for (int b = 0; b < RADIX_BITS; b++) {
+                if (b < nbits) {
+                    unsigned bm = __ballot_sync(0xffffffffu, (d[j] >> b) & 1u);
+                    pm &= ((d[j] >> b) & 1u) ? bm : ~bm;
+                }
+            }
+            m[j] = (d[j] < (uint32_t)RADIX) ? pm : (1u << lane);
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int leader = __ffs(m[j]) - 1;
@@ -319,7 +347,7 @@ template <typename KeyT> constexpr size_t onesweep_smem()
 {
     return TILE * sizeof(KeyT) + TILE * 4 + WARPS * RADIX * 4 + RADIX * 4 * 2 + WARPS * 4 + 64;
 }
-template <typename KeyT> constexpr int min_blocks() { return sizeof(KeyT) == 4 ? 3 : 2; }
+template <typename KeyT> constexpr int min_blocks() { return sizeof(KeyT) == 4 ? BWTK_RS_MINB32 : BWTK_RS_MINB64; }
 
 template <typename KeyT, typename Source>
 static int launch_pass(Source src, KeyT *kout, uint32_t *vout, int64_t n, const unsigned *d_n, const Plan &plan,
@@ -333,7 +361,7 @@ static int launch_pass(Source src, KeyT *kout, uint32_t *vout, int64_t n, const 
     }
     prof::Scope ps(sizeof(KeyT) == 4 ? "onesweep_u32" : "onesweep_u64", 2 * n * (int64_t)(sizeof(KeyT) + 4), st);
     kern<<<(unsigned)tiles, THREADS, onesweep_smem<KeyT>(), st>>>(
-        src, kout, vout, n, d_n, plan.shift[p], (1u << plan.bits[p]) - 1u, ws.ghist + p * RADIX,
+        src, kout, vout, n, d_n, plan.shift[p], plan.bits[p], ws.ghist + p * RADIX,
         ws.status + (int64_t)p * ws.max_tiles * RADIX, ws.counters + p, ws.err);
     return BWTK_OK;
 }

@@ -50,6 +50,13 @@ __device__ __forceinline__ unsigned long long rg_combine(unsigned long long a, u
     return rg_pack(ma > mb ? ma : mb, rg_sum(a) + rg_sum(b));
 }
 
+struct RgComb {
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const
+    {
+        return rg_combine(a, b);
+    }
+};
+
 // Round-0 singletons never get their rank scattered (that scatter is 46.7 M random
 // 4-byte writes for a chr21-sized contig, ~3 GB of DRAM traffic, while the doubling
 // rounds only ever read the ranks of ~10 % of the suffixes).  Their rank is their
@@ -176,42 +183,23 @@ __global__ void __launch_bounds__(RG_THREADS)
     unsigned long long excl_in_tile = rg_combine(wpre, __shfl_up_sync(0xffffffffu, inc, 1));
     if (lane == 0) excl_in_tile = wpre;
 
-    if (tid == RG_THREADS - 1) {
-        unsigned long long tile_agg = rg_combine(wpre, inc);
+    if (warp == RG_THREADS / 32 - 1) {
+        // the last warp chains the tile: lane 31 holds the tile aggregate, all 32 lanes
+        // inspect 32 predecessor tiles per round trip
+        const unsigned long long tile_agg = __shfl_sync(0xffffffffu, rg_combine(wpre, inc), 31);
         volatile unsigned long long *st = status;
         unsigned long long excl = 0;
         if (tile == 0) {
-            st[0] = RG_INCL | tile_agg;
+            if (lane == 31) st[0] = RG_INCL | tile_agg;
         } else {
-            st[tile] = RG_AGG | tile_agg;
-            int64_t t = tile - 1;
-            int spins = 0;
-            bool done = false;
-            constexpr int W = 8;   // predecessors polled per round trip
-            while (!done) {
-                unsigned long long s[W];
-#pragma unroll
-                for (int j = 0; j < W; j++) s[j] = (t - j >= 0) ? (unsigned long long)st[t - j] : (2ull << 62);
-                int used = W;
-#pragma unroll
-                for (int j = 0; j < W; j++) {
-                    if (done || used != W) continue;
-                    if ((s[j] & RG_FLAGS) == 0ull) { used = j; continue; }
-                    excl = rg_combine(s[j] & ~RG_FLAGS, excl);
-                    if (s[j] & RG_INCL) done = true;
-                }
-                if (!done) {
-                    t -= used;
-                    if (used != W) {
-                        if (++spins > rsort::SPIN_LIMIT) { *err = 2; done = true; }
-                        __nanosleep(20);
-                    }
-                }
-            }
-            st[tile] = RG_INCL | rg_combine(excl, tile_agg);
+            if (lane == 31) st[tile] = RG_AGG | tile_agg;
+            excl = warp_lookback(st, tile, RgComb{}, err, 2, rsort::SPIN_LIMIT);
+            if (lane == 31) st[tile] = RG_INCL | rg_combine(excl, tile_agg);
         }
-        s_prefix = excl;
-        if ((tile + 1) * (int64_t)RG_TILE >= m) *out_count = rg_sum(rg_combine(excl, tile_agg));
+        if (lane == 31) {
+            s_prefix = excl;
+            if ((tile + 1) * (int64_t)RG_TILE >= m) *out_count = rg_sum(rg_combine(excl, tile_agg));
+        }
     }
     __syncthreads();
     unsigned long long run = rg_combine(s_prefix, excl_in_tile);

@@ -39,6 +39,13 @@ static inline Workspace carve(Carver &c, int64_t n)
     return w;
 }
 
+struct SumComb {
+    __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const
+    {
+        return a + b;
+    }
+};
+
 template <typename Count, typename Emit>
 __global__ void __launch_bounds__(THREADS)
     scan_kernel(int64_t n, Count count, Emit emit, unsigned long long *status, unsigned *counter,
@@ -72,35 +79,21 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
     for (int w = 0; w < THREADS / 32; w++)
         if (w < warp) wpre += s_warp[w];
-    if (tid == THREADS - 1) {
-        unsigned long long tile_agg = wpre + inc;
+    if (warp == THREADS / 32 - 1) {
+        const unsigned long long tile_agg = __shfl_sync(0xffffffffu, wpre + inc, 31);
         volatile unsigned long long *st = status;
         unsigned long long excl = 0;
         if (tile == 0) {
-            st[0] = INCL | tile_agg;
+            if (lane == 31) st[0] = INCL | tile_agg;
         } else {
-            st[tile] = AGG | tile_agg;
-            int64_t t = tile - 1;
-            while (true) {
-                unsigned long long s = st[t];
-                int spins = 0;
-                while ((s & FLAGS) == 0ull) {
-                    if (++spins > SPIN_LIMIT) {
-                        *err = 3;
-                        s = INCL;
-                        break;
-                    }
-                    __nanosleep(32);
-                    s = st[t];
-                }
-                excl += s & ~FLAGS;
-                if (s & INCL) break;
-                t--;
-            }
-            st[tile] = INCL | (excl + tile_agg);
+            if (lane == 31) st[tile] = AGG | tile_agg;
+            excl = warp_lookback(st, tile, SumComb{}, err, 3, SPIN_LIMIT);
+            if (lane == 31) st[tile] = INCL | (excl + tile_agg);
         }
-        s_prefix = excl;
-        if ((tile + 1) * (int64_t)TILE >= n) *total = excl + tile_agg;
+        if (lane == 31) {
+            s_prefix = excl;
+            if ((tile + 1) * (int64_t)TILE >= n) *total = excl + tile_agg;
+        }
     }
     __syncthreads();
     unsigned long long run = s_prefix + wpre + inc - sum;
