@@ -181,6 +181,41 @@ static __global__ void scan_hist_kernel(uint32_t *ghist)
     h[threadIdx.x] = s[threadIdx.x];
 }
 
+// One step of the peer-mask refinement: keeps in `pm` the lanes whose digit agrees with
+// this lane's in bit B.  Written in PTX so that the bit test feeds both the ballot and the
+// mask selection (4 instructions per bit; the C++ form compiled to 6-9).
+template <int B> __device__ __forceinline__ unsigned refine_peers(unsigned pm, uint32_t d)
+{
+    unsigned out;
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, bm;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 bm, p, 0xffffffff;\n\t"
+        "@!p not.b32 bm, bm;\n\t"
+        "and.b32 %0, %1, bm;\n\t"
+        "}"
+        : "=r"(out)
+        : "r"(pm), "r"(d), "n"(1u << B));
+    return out;
+}
+
+// lanes of the warp whose 8-bit digit equals this lane's (all 32 lanes must call)
+__device__ __forceinline__ unsigned peers_of_digit(uint32_t d)
+{
+    unsigned pm = 0xffffffffu;
+    pm = refine_peers<0>(pm, d);
+    pm = refine_peers<1>(pm, d);
+    pm = refine_peers<2>(pm, d);
+    pm = refine_peers<3>(pm, d);
+    pm = refine_peers<4>(pm, d);
+    pm = refine_peers<5>(pm, d);
+    pm = refine_peers<6>(pm, d);
+    pm = refine_peers<7>(pm, d);
+    return pm;
+}
+
 template <typename KeyT, typename Source, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     onesweep_kernel(Source src, KeyT *__restrict__ kout, uint32_t *__restrict__ vout, int64_t n,
@@ -225,30 +260,26 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     for (int k0 = 0; k0 < ITEMS; k0 += 4) {
         uint32_t d[4];
         unsigned m[4];
+        // Slots past the end of the last tile take the top digit: they follow every real key
+        // in index order, so they rank behind the real keys of that digit and only inflate its
+        // count, which is corrected below.
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             bool valid = (warp_base + (k0 + j) * 32) < tile_n;
-            d[j] = valid ? ((uint32_t)(key[k0 + j] >> shift) & digit_mask) : (uint32_t)RADIX;
+            d[j] = valid ? ((uint32_t)(key[k0 + j] >> shift) & digit_mask) : (uint32_t)(RADIX - 1);
         }
         // peer mask of equal digits from one ballot per digit bit (MATCH.ANY runs on the
-        // address-divergence unit at ~70 cycles per warp and was the kernel's bottleneck)
+        // address-divergence unit at ~70 cycles per warp and was the kernel's bottleneck);
+        // bits above nbits are zero in every lane and leave the mask unchanged
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            unsigned pm = __ballot_sync(0xffffffffu, d[j] < (uint32_t)RADIX);
-#pragma unroll
-            for (int b = 0; b < RADIX_BITS; b++) {
-                if (b < nbits) {
-                    unsigned bm = __ballot_sync(0xffffffffu, (d[j] >> b) & 1u);
-                    pm &= ((d[j] >> b) & 1u) ? bm : ~bm;
-                }
-            }
-            m[j] = (d[j] < (uint32_t)RADIX) ? pm : (1u << lane);
+            m[j] = peers_of_digit(d[j]);
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int leader = __ffs(m[j]) - 1;
             uint32_t before = 0;
-            if (lane == leader && d[j] < (uint32_t)RADIX) before = atomicAdd(&my_hist[d[j]], (uint32_t)__popc(m[j]));
+            if (lane == leader) before = atomicAdd(&my_hist[d[j]], (uint32_t)__popc(m[j]));
             before = __shfl_sync(0xffffffffu, before, leader);
             rpos[k0 + j] = before + __popc(m[j] & lt);
         }
@@ -264,6 +295,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             s_whist[w * RADIX + tid] = cnt;
             cnt += t;
         }
+        if (tid == RADIX - 1) cnt -= (uint32_t)(TILE - tile_n);   // the padding slots of the last tile
         // exclusive scan of cnt over the 256 digits
         incl = cnt;
 #pragma unroll
