@@ -8,6 +8,8 @@
 // uint64_t.  The first pass can read its pairs from a generator (Source) instead
 // of arrays, e.g. suffix keys straight from the bit-packed text.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bwtk {
@@ -161,6 +163,55 @@ __global__ void __launch_bounds__(512) hist_kernel(Source src, int64_t n, const 
         if (v) atomicAdd(&ghist[i], v);
     }
 }
+
+// Histogram of the 8-bit chunks that start at every symbol of a bit-packed text (symbol i
+// at stream bit i*bits): the top digit of every round-0 suffix key.  One 32-bit word (32/bits
+// symbol starts) per thread step, per-warp shared histograms.
+static __global__ void __launch_bounds__(512)
+    chunk_hist_kernel(const uint32_t *__restrict__ packed, int64_t n, int bits, uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t s_h[16][RADIX];
+    for (int i = threadIdx.x; i < 16 * RADIX; i += blockDim.x) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const int per = 32 / bits;
+    const int64_t nwords = (n + per - 1) / per;
+    uint32_t *mine = s_h[threadIdx.x >> 5];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
+        const uint32_t a = __ldg(packed + w), b = __ldg(packed + w + 1);
+        const int64_t i0 = w * per;
+        const int cnt = (n - i0) < per ? (int)(n - i0) : per;
+        for (int q = 0; q < cnt; q++) atomicAdd(&mine[__funnelshift_l(b, a, q * bits) >> 24], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int w = 0; w < 16; w++) v += s_h[w][i];
+        if (v) atomicAdd(&out[i], v);
+    }
+}
+
+// Digit p of key(i) is the chunk at symbol i + k_p, k_p = (24 - 8p)/bits, and chunks that
+// start at or after the end of the text are zero: hist_p = H - (chunks of the first k_p
+// symbols) + k_p * [v == 0].  `h0` (the chunk histogram) may alias no row of `ghist` in use.
+static __global__ void shift_hist_kernel(const uint32_t *__restrict__ packed, int64_t n, int bits,
+                                         const uint32_t *__restrict__ h0, uint32_t *__restrict__ ghist)
+{
+    const uint32_t v = threadIdx.x;
+    const uint32_t base = h0[v];
+    for (int p = 0; p < 4; p++) {
+        const int k = (24 - 8 * p) / bits;
+        uint32_t c = base;
+        for (int i = 0; i < k && i < n; i++) {
+            if ((window32(packed, (int64_t)i * bits) >> 24) == v) c--;   // symbol i leaves the range ...
+            if (v == 0) c++;                                              // ... and slot n + i (all zero) enters
+        }
+        ghist[p * RADIX + v] = c;
+    }
+}
+
+static inline int64_t packed_hist_bytes(int64_t n, int bits) { return n * bits / 8 + 1; }
 
 // exclusive scan of each pass's 256 bins, in place; one block per pass
 static __global__ void scan_hist_kernel(uint32_t *ghist)
@@ -424,7 +475,21 @@ int sort_pairs_from(Source first, bool first_is_k0, KeyT *k0, uint32_t *v0, KeyT
     BWTK_CUDA(cudaMemsetAsync(ws.status, 0, (size_t)((plan.passes - 1) * ws.max_tiles + tiles) * RADIX * 4, st));
     int hgrid = (int)(ceil_div(n, 512 * 16) < NUM_SMS * 4 ? ceil_div(n, 512 * 16) : NUM_SMS * 4);
     if (hgrid < 1) hgrid = 1;
-    {
+    bool hist_done = false;
+    if constexpr (std::is_same<Source, PackedSuffixSource>::value) {
+        if (!d_n && bit_lo == 0 && bit_hi == 32 && first.used == 32 && plan.passes == 4) {
+            // suffix keys are windows of one bit stream: one chunk histogram serves all four digits
+            prof::Scope ps("radix_hist_u32", packed_hist_bytes(n, first.bits), st);
+            int cgrid = (int)(ceil_div(n, 512 * 64) < NUM_SMS * 4 ? ceil_div(n, 512 * 64) : NUM_SMS * 4);
+            chunk_hist_kernel<<<cgrid < 1 ? 1 : cgrid, 512, 0, st>>>(first.packed, n, first.bits,
+                                                                    ws.ghist + (MAX_PASSES - 1) * RADIX);
+            BWTK_LAUNCH_CHECK();
+            shift_hist_kernel<<<1, RADIX, 0, st>>>(first.packed, n, first.bits, ws.ghist + (MAX_PASSES - 1) * RADIX,
+                                                  ws.ghist);
+            hist_done = true;
+        }
+    }
+    if (!hist_done) {
         prof::Scope ps(sizeof(KeyT) == 4 ? "radix_hist_u32" : "radix_hist_u64", n * (int64_t)sizeof(KeyT), st);
         hist_kernel<KeyT, Source><<<hgrid, 512, 0, st>>>(first, n, d_n, plan, ws.ghist);
     }

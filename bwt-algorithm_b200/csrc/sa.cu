@@ -265,9 +265,10 @@ int64_t sa_core_workspace_bytes(int64_t n)
 // Suffix array of the text whose packed form (bits per symbol, `fast` = ACGT$
 // layout) is already on the device.  Synchronises the stream.
 int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_t *d_sa, int32_t *d_isa_out,
-                  void *d_ws, int64_t ws_bytes, int64_t *h_stats, cudaStream_t st)
+                  void *d_ws, int64_t ws_bytes, int64_t *h_stats, cudaStream_t st, const uint32_t **d_skey0_out)
 {
     if (h_stats) memset(h_stats, 0, 8 * sizeof(int64_t));
+    if (d_skey0_out) *d_skey0_out = nullptr;
     if (ws_bytes < sa_core_workspace_bytes(n)) {
         set_error("sa workspace: need %lld bytes, got %lld", (long long)sa_core_workspace_bytes(n),
                   (long long)ws_bytes);
@@ -321,6 +322,9 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
         if (rc) return rc;
     }
     uint32_t *skey32 = in_first ? key32a : key32b;
+    // key of the suffix at every SA position (later rounds only permute suffixes inside a
+    // group of equal keys); stays valid until the caller reuses the workspace
+    if (d_skey0_out) *d_skey0_out = skey32;
     uint32_t *sval = in_first ? val0 : val1;
     int32_t *pos_in = pos0, *pos_out = pos1;
     uint32_t *suf_other = in_first ? val1 : val0;  // free value buffer receives the active suffixes
@@ -451,5 +455,6 @@ extern "C" int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa
     int rc = prepare_text(d_text, n, packed, d_hist, totals, &bits, &fast, st);
     if (rc) return rc;
     c.off = align_up(c.off, 256);
-    return sa_build_core(packed, n, bits, fast, d_sa, d_isa_out, (char *)d_ws + c.off, ws_bytes - c.off, h_stats, st);
+    return sa_build_core(packed, n, bits, fast, d_sa, d_isa_out, (char *)d_ws + c.off, ws_bytes - c.off, h_stats, st,
+                         nullptr);
 }
