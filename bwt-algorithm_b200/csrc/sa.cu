@@ -27,8 +27,14 @@ int64_t packed_words(int64_t n, int bits);
 
 namespace sa {
 
-constexpr int RG_THREADS = 256;
-constexpr int RG_ITEMS = 8;
+#ifndef BWTK_RG_THREADS
+#define BWTK_RG_THREADS 256
+#endif
+#ifndef BWTK_RG_ITEMS
+#define BWTK_RG_ITEMS 16
+#endif
+constexpr int RG_THREADS = BWTK_RG_THREADS;
+constexpr int RG_ITEMS = BWTK_RG_ITEMS;   // a multiple of 4 (16-byte vector loads)
 constexpr int RG_TILE = RG_THREADS * RG_ITEMS;
 constexpr int MAX_ROUNDS = 40;       // 2^40 symbols of common prefix: unreachable for n < 2^30
 constexpr int ROUND_BATCH = 4;
@@ -102,6 +108,16 @@ __global__ void invert_kernel(const int32_t *__restrict__ sa, int64_t n, int32_t
     if (j < n) isa[sa[j]] = (int32_t)j;
 }
 
+__device__ __forceinline__ void unpack16(const uint4 &q, uint32_t *dst)
+{
+    dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+}
+__device__ __forceinline__ void unpack16(const uint4 &q, uint64_t *dst)
+{
+    dst[0] = ((uint64_t)q.y << 32) | q.x;
+    dst[1] = ((uint64_t)q.w << 32) | q.z;
+}
+
 // One pass over the sorted (key, suffix) list: see file header.  The element
 // count is m_host when d_m is null, else *d_m (grid sized for an upper bound).
 template <typename KeyT, bool FIRST>
@@ -116,11 +132,6 @@ __global__ void __launch_bounds__(RG_THREADS)
     __shared__ unsigned s_tile;
     __shared__ unsigned long long s_warp[RG_THREADS / 32];
     __shared__ unsigned long long s_prefix;
-    // Tile elements tile0-1 .. tile0+TILE are staged through shared memory (coalesced
-    // global loads, blocked reads); one pad slot per 8 elements keeps the stride-8
-    // blocked reads conflict-free.
-    __shared__ KeyT s_key[RG_TILE + 2 + (RG_TILE + 2) / 8 + 1];
-    __shared__ uint32_t s_suf[RG_TILE + 2 + (RG_TILE + 2) / 8 + 1];
     if (d_m) m = *d_m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
@@ -130,22 +141,51 @@ __global__ void __launch_bounds__(RG_THREADS)
     if (tile0 >= m) return;
     const int64_t t0 = tile0 + (int64_t)tid * RG_ITEMS;
 
-    for (int e = tid; e < RG_TILE + 2; e += RG_THREADS) {
-        int64_t t = tile0 - 1 + e;
-        bool ok = t >= 0 && t < m;
-        s_key[e + (e >> 3)] = ok ? skey[t] : (KeyT)0;
-        uint32_t sv = ok ? ssuf[t] : 0u;
-        s_suf[e + (e >> 3)] = sv;
-        if (FIRST && ok && e >= 1 && e <= RG_TILE) sa[t] = (int32_t)sv;   // SA[t] = sorted suffix, coalesced
-    }
-    __syncthreads();
+    // Blocked loads straight into registers: RG_ITEMS consecutive elements per thread as
+    // 16-byte vectors (the buffers are 256-byte aligned and t0 is a multiple of RG_ITEMS),
+    // plus the two neighbours t0-1 and t0+RG_ITEMS, which hit the sectors the adjacent
+    // threads fetch anyway.  k[j+1], sf[j+1] <-> element t0+j.
     KeyT k[RG_ITEMS + 2];
     uint32_t sf[RG_ITEMS + 2];
+    constexpr int KV = 16 / (int)sizeof(KeyT);   // keys per 16-byte vector
+    if (t0 + RG_ITEMS <= m) {
 #pragma unroll
-    for (int j = 0; j < RG_ITEMS + 2; j++) {
-        int e = tid * RG_ITEMS + j;
-        k[j] = s_key[e + (e >> 3)];
-        sf[j] = s_suf[e + (e >> 3)];
+        for (int v = 0; v < RG_ITEMS / KV; v++) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(skey + t0) + v);
+            unpack16(q, &k[1 + v * KV]);
+        }
+#pragma unroll
+        for (int v = 0; v < RG_ITEMS / 4; v++) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(ssuf + t0) + v);
+            sf[1 + v * 4 + 0] = q.x; sf[1 + v * 4 + 1] = q.y; sf[1 + v * 4 + 2] = q.z; sf[1 + v * 4 + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < RG_ITEMS; j++) {
+            const bool ok = t0 + j < m;
+            k[1 + j] = ok ? skey[t0 + j] : (KeyT)0;
+            sf[1 + j] = ok ? ssuf[t0 + j] : 0u;
+        }
+    }
+    {
+        const bool okp = t0 >= 1 && t0 - 1 < m, okn = t0 + RG_ITEMS < m;
+        k[0] = okp ? __ldg(skey + t0 - 1) : (KeyT)0;
+        sf[0] = okp ? __ldg(ssuf + t0 - 1) : 0u;
+        k[RG_ITEMS + 1] = okn ? __ldg(skey + t0 + RG_ITEMS) : (KeyT)0;
+        sf[RG_ITEMS + 1] = okn ? __ldg(ssuf + t0 + RG_ITEMS) : 0u;
+    }
+    if (FIRST) {
+        // SA[t] = sorted suffix: every thread stores its RG_ITEMS consecutive entries
+        if (t0 + RG_ITEMS <= m) {
+#pragma unroll
+            for (int v = 0; v < RG_ITEMS / 4; v++)
+                reinterpret_cast<int4 *>(sa + t0)[v] = make_int4((int)sf[1 + v * 4], (int)sf[2 + v * 4],
+                                                                 (int)sf[3 + v * 4], (int)sf[4 + v * 4]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < RG_ITEMS; j++)
+                if (t0 + j < m) sa[t0 + j] = (int32_t)sf[1 + j];
+        }
     }
     bool head[RG_ITEMS + 1];
 #pragma unroll
@@ -269,6 +309,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
 {
     if (h_stats) memset(h_stats, 0, 8 * sizeof(int64_t));
     if (d_skey0_out) *d_skey0_out = nullptr;
+    BWTK_REQUIRE((((uintptr_t)d_sa | (uintptr_t)d_ws) & 15) == 0, "d_sa and the workspace must be 16-byte aligned");
     if (ws_bytes < sa_core_workspace_bytes(n)) {
         set_error("sa workspace: need %lld bytes, got %lld", (long long)sa_core_workspace_bytes(n),
                   (long long)ws_bytes);
