@@ -58,14 +58,33 @@ def tier1_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str) -> Li
 def strict_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str, max_mismatch: int) -> List[TandemRepeat]:
     """Rows (start,end,primitive_period,copies) -> strict-scan records (bwt.py:1951-1996)."""
     out: List[TandemRepeat] = []
+    if len(rows) == 0:
+        return out
+    # A chr21-sized contig yields millions of short exact arrays, so this loop is the CLI's
+    # real bottleneck: MotifUtils.calculate_trf_statistics(text_arr, start, end, motif, count, 0.0)
+    # is unrolled here with its per-motif parts (composition, entropy) computed once per
+    # distinct motif and its mismatch-free arithmetic written out.
+    text = text_arr.tobytes()
+    size = len(text)
+    per_motif = {}
+    pm = (1.0 - 0.0) * 100.0
+    mm_per_copy = 0 if pm >= 99.9 else max_mismatch
     for start, end, prim, count in rows[:, :4].tolist():
-        motif = _decode(text_arr, start, start + prim)
-        pm, pi, score, comp, ent, actual = MotifUtils.calculate_trf_statistics(text_arr, start, end, motif, count, 0.0)
+        raw = text[start:start + prim]
+        known = per_motif.get(raw)
+        if known is None:
+            motif = raw.decode("ascii", errors="replace")
+            known = per_motif[raw] = (motif, MotifUtils.calculate_composition(motif),
+                                      MotifUtils.calculate_entropy(motif))
+        motif, comp, ent = known
+        length = end - start
+        actual = text[start:end].decode("ascii", errors="replace") if end <= size else motif * int(count)
+        score = max(0, int((length * (1.0 - 0.0) * 2) - (length * 0.0 * 7)))
         out.append(TandemRepeat(
-            chrom=chromosome, start=start, end=end, motif=motif, copies=float(count), length=end - start,
+            chrom=chromosome, start=start, end=end, motif=motif, copies=float(count), length=length,
             tier=2, confidence=0.95, consensus_motif=motif, mismatch_rate=0.0,
-            max_mismatches_per_copy=(0 if pm >= 99.9 else max_mismatch), n_copies_evaluated=count, strand="+",
-            percent_matches=pm, percent_indels=pi, score=score, composition=comp, entropy=ent,
+            max_mismatches_per_copy=mm_per_copy, n_copies_evaluated=count, strand="+",
+            percent_matches=pm, percent_indels=0.0, score=score, composition=dict(comp), entropy=ent,
             actual_sequence=actual, variations=None))
     return out
 

@@ -8,15 +8,14 @@ with the reference's expression order.
 """
 from __future__ import annotations
 
+import functools
 import math
 import re
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 
-def _natural_sort_key(value):
-    """Natural ordering key: digit runs compare as integers, the rest
-    case-insensitively (bwt.py:22-36)."""
+def _natural_sort_key_uncached(value):
     if value is None:
         return ()
     key = []
@@ -25,6 +24,19 @@ def _natural_sort_key(value):
             continue
         key.append((0, int(chunk)) if chunk.isdigit() else (1, chunk.lower()))
     return tuple(key)
+
+
+_natural_sort_key_cached = functools.lru_cache(maxsize=1 << 16)(_natural_sort_key_uncached)
+
+
+def _natural_sort_key(value):
+    """Natural ordering key: digit runs compare as integers, the rest
+    case-insensitively (bwt.py:22-36).  Memoised: the record sorts call it once per record
+    with a handful of distinct contig names."""
+    try:
+        return _natural_sort_key_cached(value)
+    except TypeError:      # unhashable value
+        return _natural_sort_key_uncached(value)
 
 
 _DEFAULT_COMP = {"A": 25.0, "C": 25.0, "G": 25.0, "T": 25.0}
