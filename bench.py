@@ -62,6 +62,15 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_ncu_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            return json.load(f)[kernel]["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -251,7 +260,8 @@ def run_ours(args):
         top = max(prof, key=lambda r: r["ms"])
         achieved = top["algo_bytes"] / (top["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic(top["kernel"]),
+                "peak_source": peak_src,
                 "launches_per_step": top["launches"], "avg_launch_ms": round(top["ms"] / top["launches"], 4),
                 "algo_bytes_per_launch": top["algo_bytes"] // max(top["launches"], 1)}
         extras["kernels"] = prof

@@ -346,13 +346,243 @@ __device__ bool visit_rejected(const ScanCfg &c, int p, int64_t i)
     return entropy_of(s, i, p, c.plogp, c.dim) < c.min_entropy;
 }
 
+// Full evaluation of one visit that passed the cheap tests (bwt.py:2277-2386): extension,
+// primitive-period re-extension, consensus.  A pure function of the position.  Returns
+// whether a record is emitted; *next_i is where the scan continues.  One-thread form.
+__device__ bool visit_full(const ScanCfg &c, int p, int64_t i, Tally &t, uint8_t *cons, int32_t *row,
+                           int64_t *next_i)
+{
+    const uint8_t *s = c.s;
+    const int64_t n = c.n;
+    *next_i = i + c.pos_step;
+    ExtOut o = extend_with_mismatches(s, i, p, n, c.allow_mm && p <= 64, t, cons);
+    int64_t a_len = o.array_end - o.array_start;
+    if (a_len < c.min_array_len) return false;
+    int64_t part = a_len - o.copies * p;
+    if (part < 0) part = 0;
+    int64_t eff = o.copies + (((double)part / (double)p) >= 0.75 ? 1 : 0);
+    if (!(o.copies >= c.min_copies || eff >= c.min_copies)) return false;
+    int prim = smallest_period(s, o.full_start, p);
+    int p_eff = prim < p ? prim : p;
+    o = extend_with_mismatches(s, o.full_start, p_eff, n, c.allow_mm && p_eff <= 64, t, cons);
+    a_len = o.array_end - o.array_start;
+    part = a_len - o.copies * p_eff;
+    if (part < 0) part = 0;
+    eff = o.copies + (((double)part / (double)p_eff) >= 0.75 ? 1 : 0);
+    if (o.copies < c.min_copies && eff < c.min_copies) return false;
+    int64_t tmm, mmm;
+    int64_t a_start = o.array_start, a_end = o.array_end, copies_full = o.copies, cons_start = o.full_start;
+    int64_t used = consensus(s, c.n_total, cons_start, p_eff, copies_full, t, cons, &tmm, &mmm);
+    if (!used) return false;
+    int prim2 = smallest_period_buf(cons, p_eff);
+    if (prim2 < p_eff) {
+        p_eff = prim2;
+        copies_full = (a_end - a_start) / p_eff;
+        if (copies_full < 1) copies_full = 1;
+        a_end = a_start + copies_full * p_eff;
+        cons_start = a_start;
+        used = consensus(s, c.n_total, a_start, p_eff, copies_full, t, cons, &tmm, &mmm);
+        if (!used) return false;
+    }
+    row[0] = (int32_t)a_start; row[1] = (int32_t)a_end; row[2] = p_eff;
+    row[3] = (int32_t)copies_full; row[4] = (int32_t)tmm; row[5] = (int32_t)mmm;
+    row[6] = (int32_t)cons_start; row[7] = (int32_t)used;
+    *next_i = a_end;   // jump past the array (bwt.py:2386)
+    return true;
+}
+
+// ---- warp-cooperative evaluation (periods <= 32: every large contig, bwt.py:2192-2200) ----
+// Lane q owns column q of the tally, in registers; one copy is added per step by all lanes
+// at once and the mismatch total is a warp reduction, so an extension step costs ~100 cycles
+// instead of the ~4000 of the one-thread form above.  Results are identical to Tally's.
+struct WTally {
+    uint8_t sym[SLOTS];
+    uint16_t cnt[SLOTS];
+    int nsym;
+    bool overflow;
+    __device__ __forceinline__ void reset() { nsym = 0; overflow = false; }
+    __device__ __forceinline__ void add(uint8_t b, int delta)
+    {
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < SLOTS; j++)
+            if (!done && j < nsym && sym[j] == b) { cnt[j] = (uint16_t)(cnt[j] + delta); done = true; }
+        if (done) return;
+        if (nsym >= SLOTS || delta < 0) { overflow = true; return; }
+#pragma unroll
+        for (int j = 0; j < SLOTS; j++)
+            if (j == nsym) { sym[j] = b; cnt[j] = (uint16_t)delta; }
+        nsym++;
+    }
+    __device__ __forceinline__ uint8_t best(int *best_cnt) const
+    {
+        int bc = -1;
+        uint8_t bs = 0;
+#pragma unroll
+        for (int j = 0; j < SLOTS; j++) {
+            if (j < nsym) {
+                int v = cnt[j];
+                if (v > bc || (v == bc && sym[j] < bs)) { bc = v; bs = sym[j]; }
+            }
+        }
+        *best_cnt = bc < 0 ? 0 : bc;
+        return bs;
+    }
+};
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void w_add_copy(WTally &t, const uint8_t *s, int64_t at, int p, int delta)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane < p) t.add(__ldg(s + at + lane), delta);
+}
+
+__device__ __forceinline__ int64_t w_total_mm(const WTally &t, int p, int64_t copies)
+{
+    const int lane = threadIdx.x & 31;
+    int bc = 0;
+    if (lane < p) t.best(&bc);
+    return copies * p - (int64_t)warp_sum(bc);
+}
+
+// _extend_with_mismatches by a whole warp; `cons` = this lane's consensus byte (lane < period)
+__device__ ExtOut w_extend_with_mismatches(const uint8_t *s, int64_t start_pos, int period, int64_t n, bool allow_mm,
+                                           WTally &t, uint8_t &cons)
+{
+    const int lane = threadIdx.x & 31;
+    t.reset();
+    int64_t start = start_pos, end = start_pos + period, copies = 1;
+    w_add_copy(t, s, start_pos, period, 1);
+    while (end + period <= n) {
+        w_add_copy(t, s, end, period, 1);
+        int64_t bud = allow_mm ? mm_budget(period, copies + 1) : 0;
+        if (w_total_mm(t, period, copies + 1) <= bud) { copies++; end += period; }
+        else { w_add_copy(t, s, end, period, -1); break; }
+    }
+    while (start - period >= 0) {
+        w_add_copy(t, s, start - period, period, 1);
+        int64_t bud = allow_mm ? mm_budget(period, copies + 1) : 0;
+        if (w_total_mm(t, period, copies + 1) <= bud) { copies++; start -= period; }
+        else { w_add_copy(t, s, start - period, period, -1); break; }
+    }
+    int bc;
+    cons = lane < period ? t.best(&bc) : (uint8_t)0;
+    ExtOut o;
+    o.copies = copies; o.full_start = start; o.full_end = end;
+    // partial copies: leading run of matches against the consensus, right then left
+    bool mr = lane < period && end + lane < n && __ldg(s + end + lane) == cons;
+    unsigned br = __ballot_sync(0xffffffffu, mr);
+    int pr = (~br) ? (__ffs(~br) - 1) : 32;
+    int src = period - 1 - lane;
+    uint8_t crev = __shfl_sync(0xffffffffu, cons, src < 0 ? 0 : src);
+    bool ml = lane < period && start - lane - 1 >= 0 && __ldg(s + start - lane - 1) == crev;
+    unsigned bl = __ballot_sync(0xffffffffu, ml);
+    int pl = (~bl) ? (__ffs(~bl) - 1) : 32;
+    o.array_start = start - pl;
+    o.array_end = end + pr;
+    return o;
+}
+
+// smallest period of the `len` (<= 32) bytes held one per lane
+__device__ int w_smallest_period_lanes(uint8_t c, int len)
+{
+    const int lane = threadIdx.x & 31;
+    for (int p = 1; p <= len / 2; p++) {
+        if (len % p) continue;
+        uint8_t prev = __shfl_sync(0xffffffffu, c, lane >= p ? lane - p : 0);
+        unsigned bad = __ballot_sync(0xffffffffu, lane >= p && lane < len && c != prev);
+        if (!bad) return p;
+    }
+    return len;
+}
+
+// build_consensus_motif_array by a whole warp
+__device__ int64_t w_consensus(const uint8_t *text, int64_t text_size, int64_t start, int period, int64_t copies,
+                               WTally &t, uint8_t &cons, int64_t *total_mm, int64_t *max_mm)
+{
+    const int lane = threadIdx.x & 31;
+    *total_mm = 0; *max_mm = 0;
+    if (copies <= 0 || period <= 0) return 0;
+    int64_t used = 0;
+    while (used < copies && start + (used + 1) * period <= text_size) used++;
+    if (!used) return 0;
+    t.reset();
+    for (int64_t c = 0; c < used; c++) w_add_copy(t, text, start + c * period, period, 1);
+    int bc;
+    cons = lane < period ? t.best(&bc) : (uint8_t)0;
+    for (int64_t c = 0; c < used; c++) {
+        bool ne = lane < period && __ldg(text + start + c * period + lane) != cons;
+        int64_t mm = __popc(__ballot_sync(0xffffffffu, ne));
+        *total_mm += mm;
+        if (mm > *max_mm) *max_mm = mm;
+    }
+    return used;
+}
+
+// visit_full by a whole warp (p <= 32); all outputs are warp-uniform
+__device__ bool w_visit_full(const ScanCfg &c, int p, int64_t i, int32_t *row, int64_t *next_i, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    const uint8_t *s = c.s;
+    const int64_t n = c.n;
+    WTally t;
+    uint8_t cons = 0;
+    bool emitted = false;
+    *next_i = i + c.pos_step;
+    do {
+        ExtOut o = w_extend_with_mismatches(s, i, p, n, c.allow_mm && p <= 64, t, cons);
+        int64_t a_len = o.array_end - o.array_start;
+        if (a_len < c.min_array_len) break;
+        int64_t part = a_len - o.copies * p;
+        if (part < 0) part = 0;
+        int64_t eff = o.copies + (((double)part / (double)p) >= 0.75 ? 1 : 0);
+        if (!(o.copies >= c.min_copies || eff >= c.min_copies)) break;
+        uint8_t first = lane < p ? __ldg(s + o.full_start + lane) : (uint8_t)0;
+        int prim = w_smallest_period_lanes(first, p);
+        int p_eff = prim < p ? prim : p;
+        o = w_extend_with_mismatches(s, o.full_start, p_eff, n, c.allow_mm && p_eff <= 64, t, cons);
+        a_len = o.array_end - o.array_start;
+        part = a_len - o.copies * p_eff;
+        if (part < 0) part = 0;
+        eff = o.copies + (((double)part / (double)p_eff) >= 0.75 ? 1 : 0);
+        if (o.copies < c.min_copies && eff < c.min_copies) break;
+        int64_t tmm, mmm;
+        int64_t a_start = o.array_start, a_end = o.array_end, copies_full = o.copies, cons_start = o.full_start;
+        int64_t used = w_consensus(s, c.n_total, cons_start, p_eff, copies_full, t, cons, &tmm, &mmm);
+        if (!used) break;
+        int prim2 = w_smallest_period_lanes(cons, p_eff);
+        if (prim2 < p_eff) {
+            p_eff = prim2;
+            copies_full = (a_end - a_start) / p_eff;
+            if (copies_full < 1) copies_full = 1;
+            a_end = a_start + copies_full * p_eff;
+            cons_start = a_start;
+            used = w_consensus(s, c.n_total, a_start, p_eff, copies_full, t, cons, &tmm, &mmm);
+            if (!used) break;
+        }
+        row[0] = (int32_t)a_start; row[1] = (int32_t)a_end; row[2] = p_eff;
+        row[3] = (int32_t)copies_full; row[4] = (int32_t)tmm; row[5] = (int32_t)mmm;
+        row[6] = (int32_t)cons_start; row[7] = (int32_t)used;
+        emitted = true;
+        *next_i = a_end;   // jump past the array (bwt.py:2386)
+    } while (false);
+    if (__any_sync(0xffffffffu, t.overflow)) *err = 1;
+    return emitted;
+}
+
 // One CTA per period pass.  The reference's scan visits i, i+step, ... and only
 // jumps after an emission, and every rejecting test is free of side effects, so
 // the CTA tests PASS_THREADS consecutive visits at once; the first visit that is
-// not rejected is evaluated in full by one thread (extension, consensus, record)
-// and sets the next position.  budget[pass] = visits this pass may spend
-// (MAX_ITER in the counting run).  Rows are appended to `tmp` with
-// aux = (pass, sequence number within the pass, visit index).
+// not rejected is evaluated in full by warp 0 (extension, consensus, record; one
+// thread for periods above 32) and sets the next position.  budget[pass] = visits
+// this pass may spend (MAX_ITER in the counting run).  Rows are appended to `tmp`
+// with aux = (pass, sequence number within the pass, visit index).
 __global__ void __launch_bounds__(PASS_THREADS)
     period_pass_kernel(ScanCfg c, int64_t npass, const int64_t *__restrict__ budget,
                        int64_t *__restrict__ visits, int64_t *__restrict__ emits,
@@ -370,12 +600,13 @@ __global__ void __launch_bounds__(PASS_THREADS)
     __shared__ int32_t s_memo_row[MEMO][BWTK_REC_W];
     __shared__ int64_t s_ff, s_ff_seq0, s_ff_it0, s_ff_cyc;
     __shared__ int s_ff_hit;
+    __shared__ int64_t s_ev_i, s_ev_it;
+    __shared__ int s_ev_in;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = (int)(c.min_p + pass * c.per_step);
     uint8_t *my = scratch + pass * scratch_per_thread(maxp);
     Tally t = make_tally(my, maxp);
     uint8_t *cons = t.nsym + maxp;
-    const uint8_t *s = c.s;
     const int64_t n = c.n;
     const int64_t allowed = budget ? budget[pass] : MAX_ITER;
     if (tid == 0) {
@@ -405,12 +636,15 @@ __global__ void __launch_bounds__(PASS_THREADS)
             __syncthreads();
             continue;
         }
-        if (tid == f) {
-            // visits 0..f-1 were rejected; this one either ends the scan or is evaluated in full
-            int64_t it = it0 + f, i = x;
-            s_ff = 0;
-            if (!in_range) {
-                s_i = i; s_it = it;   // loop condition fails on re-entry (end of text or budget)
+        // visits 0..f-1 were rejected; visit f either ends the scan or is evaluated in full
+        if (tid == f) { s_ev_i = x; s_ev_it = it0 + f; s_ev_in = in_range ? 1 : 0; }
+        __syncthreads();
+        if (warp == 0) {
+            int64_t it = s_ev_it;
+            const int64_t i = s_ev_i;
+            if (lane == 0) s_ff = 0;
+            if (!s_ev_in) {
+                if (lane == 0) { s_i = i; s_it = it; }   // loop condition fails on re-entry (end of text or budget)
             } else {
                 it++;
                 // The outcome of a full evaluation is a pure function of the position, and the
@@ -422,87 +656,62 @@ __global__ void __launch_bounds__(PASS_THREADS)
                 if (hit < 0) {
                     int64_t next_i = i + c.pos_step;
                     int32_t row[BWTK_REC_W];
+#pragma unroll
+                    for (int q = 0; q < BWTK_REC_W; q++) row[q] = 0;
                     bool emitted = false;
-                    do {
-                        ExtOut o = extend_with_mismatches(s, i, p, n, c.allow_mm && p <= 64, t, cons);
-                        int64_t a_len = o.array_end - o.array_start;
-                        if (a_len < c.min_array_len) break;
-                        int64_t part = a_len - o.copies * p;
-                        if (part < 0) part = 0;
-                        int64_t eff = o.copies + (((double)part / (double)p) >= 0.75 ? 1 : 0);
-                        if (!(o.copies >= c.min_copies || eff >= c.min_copies)) break;
-                        int prim = smallest_period(s, o.full_start, p);
-                        int p_eff = prim < p ? prim : p;
-                        o = extend_with_mismatches(s, o.full_start, p_eff, n, c.allow_mm && p_eff <= 64, t, cons);
-                        a_len = o.array_end - o.array_start;
-                        part = a_len - o.copies * p_eff;
-                        if (part < 0) part = 0;
-                        eff = o.copies + (((double)part / (double)p_eff) >= 0.75 ? 1 : 0);
-                        if (o.copies < c.min_copies && eff < c.min_copies) break;
-                        int64_t tmm, mmm;
-                        int64_t a_start = o.array_start, a_end = o.array_end, copies_full = o.copies,
-                                cons_start = o.full_start;
-                        int64_t used = consensus(s, c.n_total, cons_start, p_eff, copies_full, t, cons, &tmm, &mmm);
-                        if (!used) break;
-                        int prim2 = smallest_period_buf(cons, p_eff);
-                        if (prim2 < p_eff) {
-                            p_eff = prim2;
-                            copies_full = (a_end - a_start) / p_eff;
-                            if (copies_full < 1) copies_full = 1;
-                            a_end = a_start + copies_full * p_eff;
-                            cons_start = a_start;
-                            used = consensus(s, c.n_total, a_start, p_eff, copies_full, t, cons, &tmm, &mmm);
-                            if (!used) break;
-                        }
-                        row[0] = (int32_t)a_start; row[1] = (int32_t)a_end; row[2] = p_eff;
-                        row[3] = (int32_t)copies_full; row[4] = (int32_t)tmm; row[5] = (int32_t)mmm;
-                        row[6] = (int32_t)cons_start; row[7] = (int32_t)used;
-                        emitted = true;
-                        next_i = a_end;   // jump past the array (bwt.py:2386)
-                    } while (false);
-                    if (t.overflow) *err = 1;
+                    if (p <= 32) {
+                        emitted = w_visit_full(c, p, i, row, &next_i, err);
+                    } else if (lane == 0) {
+                        emitted = visit_full(c, p, i, t, cons, row, &next_i);
+                        if (t.overflow) *err = 1;
+                    }
                     hit = s_memo_next % MEMO;
-                    s_memo_next++;
-                    s_memo_x[hit] = i;
-                    s_memo_ni[hit] = next_i;
-                    s_memo_emit[hit] = emitted ? 1 : 0;
-                    s_memo_it[hit] = -1;
-                    for (int q = 0; q < BWTK_REC_W; q++) s_memo_row[hit][q] = emitted ? row[q] : 0;
+                    __syncwarp();
+                    if (lane == 0) {
+                        s_memo_next++;
+                        s_memo_x[hit] = i;
+                        s_memo_ni[hit] = next_i;
+                        s_memo_emit[hit] = emitted ? 1 : 0;
+                        s_memo_it[hit] = -1;
+                        for (int q = 0; q < BWTK_REC_W; q++) s_memo_row[hit][q] = emitted ? row[q] : 0;
+                    }
                 }
-                int64_t seq = s_seq;
-                const bool emitted = s_memo_emit[hit] != 0;
-                if (emitted) {
-                    if (tmp) {
-                        unsigned long long slot = atomicAdd(tmp_count, 1ull);
-                        if ((int64_t)slot < tmp_cap) {
-                            int32_t *row = tmp + slot * BWTK_REC_W;
-                            for (int q = 0; q < BWTK_REC_W; q++) row[q] = s_memo_row[hit][q];
-                            int32_t *ax = tmp_aux + slot * 4;
-                            ax[0] = (int32_t)pass; ax[1] = (int32_t)seq; ax[2] = (int32_t)it; ax[3] = 0;
+                if (lane == 0) {
+                    int64_t seq = s_seq;
+                    const bool emitted = s_memo_emit[hit] != 0;
+                    if (emitted) {
+                        if (tmp) {
+                            unsigned long long slot = atomicAdd(tmp_count, 1ull);
+                            if ((int64_t)slot < tmp_cap) {
+                                int32_t *row = tmp + slot * BWTK_REC_W;
+                                for (int q = 0; q < BWTK_REC_W; q++) row[q] = s_memo_row[hit][q];
+                                int32_t *ax = tmp_aux + slot * 4;
+                                ax[0] = (int32_t)pass; ax[1] = (int32_t)seq; ax[2] = (int32_t)it; ax[3] = 0;
+                            }
+                        }
+                        seq++;
+                    }
+                    // Simple cycle: the same position was the previous full evaluation too, so the
+                    // visits in between repeat verbatim; skip whole cycles up to the budget.
+                    if (s_last_full == hit && s_memo_it[hit] >= 0) {
+                        int64_t cyc = it - s_memo_it[hit];
+                        int64_t reps = cyc > 0 ? (allowed - it) / cyc : 0;
+                        if (reps > 0) {
+                            s_ff = emitted ? reps : 0;
+                            s_ff_hit = hit;
+                            s_ff_seq0 = seq;
+                            s_ff_it0 = it;
+                            s_ff_cyc = cyc;
+                            it += reps * cyc;
+                            if (emitted) seq += reps;
                         }
                     }
-                    seq++;
+                    s_memo_it[hit] = it;
+                    s_last_full = hit;
+                    s_seq = seq;
+                    s_i = s_memo_ni[hit];
+                    s_it = it;
                 }
-                // Simple cycle: the same position was the previous full evaluation too, so the
-                // visits in between repeat verbatim; skip whole cycles up to the budget.
-                if (s_last_full == hit && s_memo_it[hit] >= 0) {
-                    int64_t cyc = it - s_memo_it[hit];
-                    int64_t reps = cyc > 0 ? (allowed - it) / cyc : 0;
-                    if (reps > 0) {
-                        s_ff = emitted ? reps : 0;
-                        s_ff_hit = hit;
-                        s_ff_seq0 = seq;
-                        s_ff_it0 = it;
-                        s_ff_cyc = cyc;
-                        it += reps * cyc;
-                        if (emitted) seq += reps;
-                    }
-                }
-                s_memo_it[hit] = it;
-                s_last_full = hit;
-                s_seq = seq;
-                s_i = s_memo_ni[hit];
-                s_it = it;
             }
         }
         __syncthreads();

@@ -252,9 +252,9 @@ __device__ int64_t would_emit(const Params &p, int64_t i)
     if (i >= n - m) return -1;
     if (p.seen[i]) return -1;
     const uint8_t *t = p.text;
-    for (int q = 0; q < m; q++)
-        if (!acgt(__ldg(t + i + q))) return -1;
-    // run of text[j] == text[j+m] from i; copies = 1 + run/m
+    // run of text[j] == text[j+m] from i; copies = 1 + run/m.  Tested before the ACGT check
+    // of the motif: on non-repetitive sequence the run ends after one or two symbols.
+    if (!acgt(__ldg(t + i))) return -1;   // keeps N blocks (megabases in real assemblies) from being walked
     int64_t lim = n - m;
     int64_t need = (int64_t)(p.mc - 1) * m;
     int64_t j = i;
@@ -263,6 +263,8 @@ __device__ int64_t would_emit(const Params &p, int64_t i)
     }
     int64_t run = j - i;
     if (run < need) return -1;
+    for (int q = 1; q < m; q++)
+        if (!acgt(__ldg(t + i + q))) return -1;
     int64_t copies = 1 + run / m;
     if (copies < p.mc) return -1;
     int64_t length = copies * m;
