@@ -6,7 +6,14 @@
 //   Count  : __device__ uint64_t operator()(int64_t i)            (items at i)
 //   Emit   : __device__ void operator()(int64_t i, uint64_t excl, uint64_t cnt)
 // Counts are summed in 62 bits, so two 31-bit counters may be packed in one value.
+// A Count that declares a nested type `Ctx` gets one default-constructed Ctx per thread,
+// shared by its ITEMS consecutive elements and by both phases:
+//   Count  : operator()(int64_t i, int k, Ctx &)      Emit : operator()(i, k, excl, cnt, Ctx &)
+// (k = 0..ITEMS-1, the element's slot in the thread), so that what the count phase computed
+// can be reused by the next element and by the emit phase.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bwtk {
@@ -39,6 +46,16 @@ static inline Workspace carve(Carver &c, int64_t n)
     return w;
 }
 
+struct NoCtx {};
+template <typename F, typename = void> struct CtxOf {
+    using type = NoCtx;
+    static constexpr bool has = false;
+};
+template <typename F> struct CtxOf<F, std::void_t<typename F::Ctx>> {
+    using type = typename F::Ctx;
+    static constexpr bool has = true;
+};
+
 struct SumComb {
     __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const
     {
@@ -61,10 +78,15 @@ __global__ void __launch_bounds__(THREADS)
     const int64_t i0 = tile * TILE + (int64_t)tid * ITEMS;
     unsigned long long c[ITEMS];
     unsigned long long sum = 0;
+    typename CtxOf<Count>::type ctx;
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         int64_t i = i0 + k;
-        c[k] = i < n ? (unsigned long long)count(i) : 0ull;
+        c[k] = 0ull;
+        if (i < n) {
+            if constexpr (CtxOf<Count>::has) c[k] = (unsigned long long)count(i, k, ctx);
+            else c[k] = (unsigned long long)count(i);
+        }
         sum += c[k];
     }
     unsigned long long inc = sum;
@@ -100,7 +122,10 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         int64_t i = i0 + k;
-        if (i < n) emit(i, run, c[k]);
+        if (i < n) {
+            if constexpr (CtxOf<Count>::has) emit(i, k, run, c[k], ctx);
+            else emit(i, run, c[k]);
+        }
         run += c[k];
     }
 }

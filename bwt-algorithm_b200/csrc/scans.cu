@@ -245,21 +245,30 @@ __device__ __forceinline__ bool acgt(uint8_t c) { return c == 'A' || c == 'C' ||
 // "Would the reference emit a repeat if its scan visited position i in this
 // pass?" (bwt.py:1454-1527, with the pre-pass seen mask).  Returns the array
 // end, or -1.
-__device__ int64_t would_emit(const Params &p, int64_t i)
+//
+// `mis` carries the end of the last run walked by this thread (first j with
+// text[j] != text[j+m], or n-m): the thread's next, adjacent positions lie inside that run
+// and reuse it instead of walking again -- inside a repeat array every position would
+// otherwise walk to the array's end, and the whole CTA waits for those threads.
+__device__ int64_t would_emit(const Params &p, int64_t i, int64_t &mis)
 {
     const int m = p.m;
     const int64_t n = p.n;
     if (i >= n - m) return -1;
     if (p.seen[i]) return -1;
     const uint8_t *t = p.text;
+    if (!acgt(__ldg(t + i))) return -1;   // keeps N blocks (megabases in real assemblies) from being walked
     // run of text[j] == text[j+m] from i; copies = 1 + run/m.  Tested before the ACGT check
     // of the motif: on non-repetitive sequence the run ends after one or two symbols.
-    if (!acgt(__ldg(t + i))) return -1;   // keeps N blocks (megabases in real assemblies) from being walked
     int64_t lim = n - m;
     int64_t need = (int64_t)(p.mc - 1) * m;
-    int64_t j = i;
-    while (j < lim && __ldg(t + j) == __ldg(t + j + m)) {
-        j++;
+    int64_t j = mis;
+    if (j <= i) {
+        j = i;
+        while (j < lim && __ldg(t + j) == __ldg(t + j + m)) {
+            j++;
+        }
+        mis = j;
     }
     int64_t run = j - i;
     if (run < need) return -1;
@@ -289,15 +298,27 @@ __device__ int64_t would_emit(const Params &p, int64_t i)
 // Tier 1 candidate functor: end of the array the reference would emit at i, or -1
 struct Tier1Cand {
     Params p;
-    __device__ int64_t operator()(int64_t i) const { return would_emit(p, i); }
+    struct State { int64_t mis = -1; };
+    __device__ int64_t operator()(int64_t i, State &st) const { return would_emit(p, i, st.mis); }
 };
 
 // ---- generic greedy replay ---------------------------------------------------
 // Cand: __device__ int64_t operator()(int64_t i)  -> array end if the reference's
 //       scan would emit when it visits i (a pure function of the pre-pass state), else -1
+// State: per-thread scratch the candidate test may keep across the thread's adjacent positions.
+// The array end found in the count phase is kept for the emit phase (scan.cuh Ctx).
+template <typename Cand> struct CandCtx {
+    int64_t end[scan::ITEMS];
+    typename Cand::State st;
+};
 template <typename Cand> struct CountCand {
+    using Ctx = CandCtx<Cand>;
     Cand c;
-    __device__ uint64_t operator()(int64_t i) const { return c(i) >= 0 ? 1ull : 0ull; }
+    __device__ uint64_t operator()(int64_t i, int k, Ctx &ctx) const
+    {
+        ctx.end[k] = c(i, ctx.st);
+        return ctx.end[k] >= 0 ? 1ull : 0ull;
+    }
 };
 template <typename Cand> struct EmitCand {
     Cand c;
@@ -307,11 +328,11 @@ template <typename Cand> struct EmitCand {
     int abits;
     unsigned long long *ckey;  // (pos % step) << abits | pos
     uint32_t *cidx;
-    __device__ void operator()(int64_t i, uint64_t excl, uint64_t cnt) const
+    __device__ void operator()(int64_t i, int k, uint64_t excl, uint64_t cnt, CandCtx<Cand> &ctx) const
     {
         if (!cnt) return;
         cpos[excl] = (int32_t)i;
-        cend[excl] = (int32_t)c(i);
+        cend[excl] = (int32_t)ctx.end[k];
         ckey[excl] = ((unsigned long long)(i % step) << abits) | (unsigned long long)i;
         cidx[excl] = (uint32_t)excl;
     }
@@ -524,7 +545,8 @@ struct StrictMMCand {
     const uint8_t *text;
     int64_t n;   // without the trailing '$'
     int64_t u, mm, mc;
-    __device__ int64_t operator()(int64_t i) const
+    struct State {};
+    __device__ int64_t operator()(int64_t i, State &) const
     {
         if (i + u * mc > n) return -1;
         int64_t count = 1;
