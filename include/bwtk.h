@@ -79,7 +79,8 @@ int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa, int32_t *
  * the text has more distinct bytes the call returns BWTK_EOVERFLOW with the
  * row count in h_stats[7].  h_stats as in bwtk_sa_build (+ [7] = Occ rows).
  * Host syncs: the alphabet read-back and one per batch of doubling rounds; the
- * BWT/Occ/LCP kernels are left in flight on the stream. */
+ * BWT/Occ/LCP kernels are left in flight on the stream.  d_sa and d_ws must be
+ * 16-byte aligned (every cudaMalloc'ed pointer is); BWTK_EINVAL otherwise. */
 int64_t bwtk_index_workspace_bytes(int64_t n);
 int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t occ_rate, int32_t *d_sa, int32_t *d_isa,
                          uint8_t *d_bwt, int32_t *d_occ, int32_t occ_rows_cap, int32_t *d_lcp,
