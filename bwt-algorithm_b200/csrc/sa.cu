@@ -11,14 +11,16 @@
 //   regroup : head flags -> group-head position (max-scan) -> rank[] scatter,
 //             SA write, compaction of suffixes whose group is not yet a
 //             singleton (one single-pass decoupled look-back scan);
-//   round r : for the active suffixes only, key = (group head, rank[i+h]+1),
-//             LSD radix sort, regroup; h doubles.  Stops when nothing is active.
+//   round r : for the active suffixes only, every group is ordered by
+//             rank[i+h]+1: an LSD radix sort of (group head, rank) while the
+//             active list is long, a shared-memory segmented sort (whole groups
+//             per CTA, see segsort_kernel) once it is short enough for the radix
+//             passes to be launch-bound; then regroup; h doubles.  Stops when
+//             nothing is active.
 //
-// The active count of every round stays in device memory: after round 0 the
-// host reads it once, then launches rounds in batches whose grids are sized for
-// the last known count (counts only shrink) and reads the count again after the
-// batch.  The result is the unique suffix array, so it is bit-identical to the
-// reference's regardless of the refinement path taken.
+// The host reads the active count once per round (4 bytes) to size the grids and
+// to pick the sort.  The result is the unique suffix array, so it is bit-identical
+// to the reference's regardless of the refinement path taken.
 #include "radix_sort.cuh"
 
 namespace bwtk {
@@ -37,7 +39,6 @@ constexpr int RG_THREADS = BWTK_RG_THREADS;
 constexpr int RG_ITEMS = BWTK_RG_ITEMS;   // a multiple of 4 (16-byte vector loads)
 constexpr int RG_TILE = RG_THREADS * RG_ITEMS;
 constexpr int MAX_ROUNDS = 40;       // 2^40 symbols of common prefix: unreachable for n < 2^30
-constexpr int ROUND_BATCH = 4;
 
 // 64-bit look-back status: [63:62] flag, [61:31] (max head position + 1), [30:0] active count
 constexpr unsigned long long RG_AGG = 1ull << 62;
@@ -99,6 +100,189 @@ __global__ void build_keys_kernel(const uint32_t *__restrict__ suf, const int32_
     int64_t s = (int64_t)suf[t] + h;
     uint64_t k2 = s < n ? (uint64_t)(lr(s) + 1) : 0ull;
     key[t] = ((uint64_t)(uint32_t)grp[t] << kbits) | k2;
+}
+
+// ---- segmented sort of one doubling round -------------------------------------------
+// The active list is grouped (elements of one group are adjacent, grp[] = the group's head
+// SA position, increasing along the list), and a round only has to order every group by
+// k2 = rank[suffix + h] + 1.  After round 0 almost all groups are tiny, so instead of
+// seven global radix passes over (grp, k2) each CTA sorts a window of whole groups in
+// shared memory with one bitonic network over (grp, k2, original slot):
+//   * CTA b owns the groups whose first element lies in [b*SS_T, (b+1)*SS_T); its window
+//     runs from its first group head to the end of the group that contains its last
+//     nominal element (<= SS_W elements);
+//   * if that last group makes the window overflow it is deferred: groups of up to
+//     SS_MID_MAX elements go on a list sorted by midsort_kernel, one CTA per group;
+//     larger ones raise ctl->huge and the host redoes this round with the radix path.
+// Output: key_out = (grp << kbits) | k2 and suf_out in sorted order at the same list slots
+// (what regroup_kernel consumes).
+// k2[t] = rank[suffix + h] + 1 of every active element, one thread each: the lazy-rank lookup
+// is a chain of dependent loads, hidden only by running all elements at once (inside the
+// sort CTAs, 8 lookups per thread in sequence cost more than the sort itself)
+__global__ void build_k2_kernel(const uint32_t *__restrict__ suf, LazyRank lr, const unsigned *__restrict__ d_m,
+                                int64_t n, int64_t h, uint32_t *__restrict__ k2)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)*d_m) return;
+    int64_t s = (int64_t)suf[t] + h;
+    k2[t] = s < n ? (uint32_t)(lr(s) + 1) : 0u;
+}
+
+constexpr int SS_THREADS = 1024;
+constexpr int SS_T = 1024;
+constexpr int SS_W = 2048;
+constexpr int SS_MID_MAX = 16384;
+constexpr int SS_MID_CAP = 4096;
+constexpr int SS_MID_THREADS = 1024;
+#ifndef BWTK_SEG_MAX
+#define BWTK_SEG_MAX 1000000
+#endif
+constexpr int64_t SEG_MAX = BWTK_SEG_MAX;   // longest active list handled by the segmented sort
+
+struct SegCtl {
+    unsigned mid_count;
+    unsigned huge;
+    unsigned mid_start[SS_MID_CAP];
+    unsigned mid_size[SS_MID_CAP];
+};
+
+// bitonic sort of N (power of two) (hi, lo) pairs in shared memory, ascending by (hi, lo)
+template <int THREADS, bool HAS_HI>
+__device__ __forceinline__ void bitonic_sort(uint32_t *hi, unsigned long long *lo, int N)
+{
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (N >> 1); i += THREADS) {
+                const int a = 2 * i - (i & (j - 1)), b = a + j;
+                const bool up = (a & k) == 0;
+                const unsigned long long la = lo[a], lb = lo[b];
+                bool gt;
+                if (HAS_HI) {
+                    const uint32_t ha = hi[a], hb = hi[b];
+                    gt = ha > hb || (ha == hb && la > lb);
+                    if (gt == up) { hi[a] = hb; hi[b] = ha; }
+                } else {
+                    gt = la > lb;
+                }
+                if (gt == up) { lo[a] = lb; lo[b] = la; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
+    segsort_kernel(const uint32_t *__restrict__ suf, const int32_t *__restrict__ grp,
+                   const uint32_t *__restrict__ k2in, const unsigned *__restrict__ d_m, int kbits,
+                   uint64_t *__restrict__ key_out, uint32_t *__restrict__ suf_out, SegCtl *ctl)
+{
+    __shared__ uint32_t s_hi[SS_W];
+    __shared__ unsigned long long s_lo[SS_W];
+    __shared__ uint32_t s_suf[SS_W];
+    __shared__ int s_first, s_lasthead, s_end;
+    const int64_t m = *d_m;
+    const int64_t t0 = (int64_t)blockIdx.x * SS_T;
+    if (t0 >= m) return;
+    const int64_t t1 = t0 + SS_T < m ? t0 + SS_T : m;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_first = 0x7fffffff; s_lasthead = -1; s_end = 0x7fffffff; }
+    __syncthreads();
+    // group heads inside the nominal range
+    for (int e = tid; e < (int)(t1 - t0); e += SS_THREADS) {
+        const int64_t t = t0 + e;
+        if (t == 0 || grp[t] != grp[t - 1]) { atomicMin(&s_first, e); atomicMax(&s_lasthead, e); }
+    }
+    __syncthreads();
+    if (s_first == 0x7fffffff) return;   // the whole range belongs to a group that started earlier
+    const int64_t w0 = t0 + s_first;     // first owned element
+    const int64_t gl = t0 + s_lasthead;  // head of the group holding the last nominal element
+    const int32_t g_last = grp[gl];
+    // end of that group: first t >= t1 with another grp (bounded: beyond SS_MID_MAX it is "huge")
+    bool huge = false;
+    for (int64_t off = 0;; off += SS_THREADS) {
+        const int64_t t = t1 + off + tid;
+        const bool same = t < m && grp[t] == g_last;
+        if (!same) atomicMin(&s_end, (int)(off + tid));
+        __syncthreads();
+        const int found = s_end;
+        __syncthreads();   // nobody updates s_end for the next chunk before everyone has read it
+        if (found != 0x7fffffff) break;
+        if (t1 + off + SS_THREADS - gl > SS_MID_MAX) { huge = true; break; }
+    }
+    int64_t wend = t1 + (huge ? 0 : s_end);   // end of the last group (if known)
+    if (huge || wend - w0 > SS_W) {
+        // defer the last group; the window keeps the groups before it
+        if (tid == 0) {
+            if (huge || wend - gl > SS_MID_MAX) {
+                atomicExch(&ctl->huge, 1u);
+            } else {
+                unsigned slot = atomicAdd(&ctl->mid_count, 1u);
+                if (slot < (unsigned)SS_MID_CAP) { ctl->mid_start[slot] = (unsigned)gl; ctl->mid_size[slot] = (unsigned)(wend - gl); }
+                else atomicExch(&ctl->huge, 1u);
+            }
+        }
+        wend = gl;
+    }
+    const int len = (int)(wend - w0);
+    if (len <= 0) return;
+    int N = 32;
+    while (N < len) N <<= 1;
+    for (int e = tid; e < N; e += SS_THREADS) {
+        if (e < len) {
+            const int64_t t = w0 + e;
+            const unsigned long long k2 = k2in[t];
+            s_suf[e] = suf[t];
+            s_hi[e] = (uint32_t)grp[t];
+            s_lo[e] = (k2 << 11) | (unsigned long long)e;
+        } else {
+            s_hi[e] = 0xffffffffu;
+            s_lo[e] = ~0ull;
+        }
+    }
+    __syncthreads();
+    bitonic_sort<SS_THREADS, true>(s_hi, s_lo, N);
+    for (int e = tid; e < len; e += SS_THREADS) {
+        const unsigned long long lo = s_lo[e];
+        key_out[w0 + e] = ((uint64_t)s_hi[e] << kbits) | (uint64_t)(lo >> 11);
+        suf_out[w0 + e] = s_suf[(int)(lo & 2047ull)];
+    }
+}
+
+// one CTA per deferred group (SS_W < window, size <= SS_MID_MAX): all of it in shared memory
+__global__ void __launch_bounds__(SS_MID_THREADS)
+    midsort_kernel(const uint32_t *__restrict__ suf, const int32_t *__restrict__ grp,
+                   const uint32_t *__restrict__ k2in, int kbits, uint64_t *__restrict__ key_out,
+                   uint32_t *__restrict__ suf_out, const SegCtl *__restrict__ ctl)
+{
+    extern __shared__ __align__(16) unsigned char ss_raw[];
+    unsigned long long *s_lo = reinterpret_cast<unsigned long long *>(ss_raw);
+    uint32_t *s_suf = reinterpret_cast<uint32_t *>(ss_raw + (size_t)SS_MID_MAX * 8);
+    unsigned count = ctl->mid_count;
+    if (count > (unsigned)SS_MID_CAP) count = SS_MID_CAP;
+    for (unsigned g = blockIdx.x; g < count; g += gridDim.x) {
+        const int64_t w0 = ctl->mid_start[g];
+        const int len = (int)ctl->mid_size[g];
+        const uint64_t ghead = (uint64_t)(uint32_t)grp[w0];
+        int N = 32;
+        while (N < len) N <<= 1;
+        for (int e = threadIdx.x; e < N; e += SS_MID_THREADS) {
+            if (e < len) {
+                const unsigned long long k2 = k2in[w0 + e];
+                s_suf[e] = suf[w0 + e];
+                s_lo[e] = (k2 << 14) | (unsigned long long)e;
+            } else {
+                s_lo[e] = ~0ull;
+            }
+        }
+        __syncthreads();
+        bitonic_sort<SS_MID_THREADS, false>(nullptr, s_lo, N);
+        for (int e = threadIdx.x; e < len; e += SS_MID_THREADS) {
+            const unsigned long long lo = s_lo[e];
+            key_out[w0 + e] = (ghead << kbits) | (uint64_t)(lo >> 14);
+            suf_out[w0 + e] = s_suf[(int)(lo & 16383ull)];
+        }
+        __syncthreads();
+    }
 }
 
 // isa[sa[j]] = j (only when the caller asks for the inverse suffix array)
@@ -298,7 +482,7 @@ int64_t sa_core_workspace_bytes(int64_t n)
     b += align_up(n * 4, 256);                        // group heads
     b += align_up(ceil_div(n, sa::RG_TILE) * 8 + 256, 256);  // regroup status
     b += rsort::workspace_bytes(n);
-    b += 8192;                                        // counters
+    b += 8192 + align_up((int64_t)sizeof(sa::SegCtl), 256);  // counters, segmented-sort control block
     return b;
 }
 
@@ -338,6 +522,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     unsigned long long *rg_status = c.take<unsigned long long>(rg_tiles_max + 8);
     rsort::Workspace rws = rsort::carve(c, n);
     unsigned *counters = c.take<unsigned>(sa::MAX_ROUNDS + 8);  // [0] regroup tile id, [1+r] active count entering round r
+    sa::SegCtl *ctl = c.take<sa::SegCtl>(1);
     if (!c.ok()) {
         set_error("sa workspace carve overflow");
         return BWTK_EWORKSPACE;
@@ -393,44 +578,84 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     const sa::LazyRank lr{abits, rank, skey32, ptab, d_sa, packed, bits};
     int64_t h = S;
     int round = 1;   // next round index; its count is d_counts[round]
-    while (h_count > 0) {
-        const int64_t bound = h_count;   // counts only shrink
-        int launched = 0;
-        for (; launched < sa::ROUND_BATCH && round < sa::MAX_ROUNDS; launched++, round++) {
-            const unsigned *d_m = d_counts + round;
-            {
-                prof::Scope ps("build_keys_kernel", bound * 20, st);
-                sa::build_keys_kernel<<<(unsigned)ceil_div(bound, 256), 256, 0, st>>>(suf_in, grp, lr, d_m, n, h, kbits,
-                                                                                     keyA);
-            }
-            BWTK_LAUNCH_CHECK();
-            int rc = rsort::sort_pairs<uint64_t>(keyA, suf_in, keyB, suf_free, bound, 0, kbits + gbits, rws, st,
-                                                 &in_first, &passes, d_m);
-            if (rc) return rc;
-            uint64_t *sk = in_first ? keyA : keyB;
-            uint32_t *ss = in_first ? suf_in : suf_free;
-            uint32_t *sn = in_first ? suf_free : suf_in;  // the other value buffer takes the next list
-            int64_t tiles = ceil_div(bound, sa::RG_TILE);
-            BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
-            BWTK_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned), st));
-            {
-                prof::Scope ps("regroup_round", bound * 36, st);
-                sa::regroup_kernel<uint64_t, false><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
-                    sk, ss, pos_in, bound, d_m, 0, d_sa, rank, pos_out, sn, grp, nullptr, nullptr, rg_status, counters,
-                    d_counts + round + 1, rws.err);
-            }
-            BWTK_LAUNCH_CHECK();
-            suf_in = sn;
-            suf_free = ss;
-            { int32_t *t = pos_in; pos_in = pos_out; pos_out = t; }
-            h <<= 1;
+    static bool mid_attr = false;
+    const size_t mid_smem = (size_t)sa::SS_MID_MAX * 12;
+    if (!mid_attr) {
+        BWTK_CUDA(cudaFuncSetAttribute(sa::midsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
+        mid_attr = true;
+    }
+    while (true) {
+        const unsigned *d_m = d_counts + round;
+        if (round > 1) {   // round 1's count was read after the first regroup
+            BWTK_CUDA(cudaMemcpyAsync(&h_count, d_m, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            BWTK_CUDA(cudaStreamSynchronize(st));
         }
-        BWTK_CUDA(cudaMemcpyAsync(&h_count, d_counts + round, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        BWTK_CUDA(cudaStreamSynchronize(st));
-        if (h_count > 0 && (round >= sa::MAX_ROUNDS || h > 4 * n)) {
+        if (h_count == 0) break;
+        if (round >= sa::MAX_ROUNDS || h > 4 * n) {
             set_error("suffix array refinement did not converge");
             return BWTK_EINTERNAL;
         }
+        const int64_t bound = h_count;
+        // Every group is ordered by rank[suffix + h].  Long lists go through the radix sort
+        // (bandwidth-bound, ~7 passes); below SEG_MAX elements the passes are launch- and
+        // latency-bound and the shared-memory segmented sort (segsort_kernel) is cheaper.
+        const bool seg = bound <= sa::SEG_MAX;
+        unsigned h_ctl[2] = {0, 1};   // [1] != 0: use the radix path
+        if (seg) {
+            BWTK_CUDA(cudaMemsetAsync(ctl, 0, 8, st));
+            uint32_t *k2buf = reinterpret_cast<uint32_t *>(keyA);   // keyA is only used by the radix path
+            {
+                prof::Scope ps("build_k2_kernel", bound * 12, st);
+                sa::build_k2_kernel<<<(unsigned)ceil_div(bound, 256), 256, 0, st>>>(suf_in, lr, d_m, n, h, k2buf);
+            }
+            BWTK_LAUNCH_CHECK();
+            {
+                prof::Scope ps("segsort_kernel", bound * 28, st);
+                sa::segsort_kernel<<<(unsigned)ceil_div(bound, sa::SS_T), sa::SS_THREADS, 0, st>>>(
+                    suf_in, grp, k2buf, d_m, kbits, keyB, suf_free, ctl);
+            }
+            BWTK_LAUNCH_CHECK();
+            {
+                prof::Scope ps("midsort_kernel", 0, st);
+                sa::midsort_kernel<<<64, sa::SS_MID_THREADS, mid_smem, st>>>(suf_in, grp, k2buf, kbits, keyB, suf_free,
+                                                                           ctl);
+            }
+            BWTK_LAUNCH_CHECK();
+            BWTK_CUDA(cudaMemcpyAsync(h_ctl, ctl, 8, cudaMemcpyDeviceToHost, st));
+            BWTK_CUDA(cudaStreamSynchronize(st));
+        }
+        uint64_t *sk = keyB;
+        uint32_t *ss = suf_free, *sn = suf_in;
+        if (h_ctl[1]) {
+            // long list, or a group larger than one CTA's shared memory: radix sort of (group, k2)
+            {
+                prof::Scope ps("build_keys_kernel", (int64_t)h_count * 20, st);
+                sa::build_keys_kernel<<<(unsigned)ceil_div((int64_t)h_count, 256), 256, 0, st>>>(suf_in, grp, lr, d_m, n, h,
+                                                                                                kbits, keyA);
+            }
+            BWTK_LAUNCH_CHECK();
+            int rc = rsort::sort_pairs<uint64_t>(keyA, suf_in, keyB, suf_free, h_count, 0, kbits + gbits, rws, st,
+                                                 &in_first, &passes, d_m);
+            if (rc) return rc;
+            sk = in_first ? keyA : keyB;
+            ss = in_first ? suf_in : suf_free;
+            sn = in_first ? suf_free : suf_in;  // the other value buffer takes the next list
+        }
+        int64_t tiles = ceil_div((int64_t)h_count, sa::RG_TILE);
+        BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
+        BWTK_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned), st));
+        {
+            prof::Scope ps("regroup_round", (int64_t)h_count * 36, st);
+            sa::regroup_kernel<uint64_t, false><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
+                sk, ss, pos_in, h_count, d_m, 0, d_sa, rank, pos_out, sn, grp, nullptr, nullptr, rg_status, counters,
+                d_counts + round + 1, rws.err);
+        }
+        BWTK_LAUNCH_CHECK();
+        suf_in = sn;
+        suf_free = ss;
+        { int32_t *t = pos_in; pos_in = pos_out; pos_out = t; }
+        h <<= 1;
+        round++;
     }
     if (d_isa_out) {
         prof::Scope ps("invert_kernel", n * 8, st);

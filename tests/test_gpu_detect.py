@@ -29,7 +29,7 @@ def _scan_texts():
     return out
 
 
-@pytest.mark.parametrize("name,text", _scan_texts())
+@pytest.mark.parametrize("name,text", _scan_texts(), ids=[c[0] for c in _scan_texts()])
 def test_tier1_rows(detect, oracle, name, text):
     for t in (text, text.rstrip(b"$")):
         if not t:
@@ -42,7 +42,7 @@ def test_tier1_rows(detect, oracle, name, text):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("name,text", _scan_texts())
+@pytest.mark.parametrize("name,text", _scan_texts(), ids=[c[0] for c in _scan_texts()])
 def test_strict_rows_worker_call(detect, oracle, name, text):
     n = len(text.rstrip(b"$"))
     eff = max(120, min(n // 3, 1000))
@@ -68,7 +68,7 @@ def test_strict_rows_150k(detect, oracle):
     assert len(got) > 5000
 
 
-@pytest.mark.parametrize("name,text", _scan_texts())
+@pytest.mark.parametrize("name,text", _scan_texts(), ids=[c[0] for c in _scan_texts()])
 def test_plateau_rows(detect, oracle, name, text):
     sa = oracle.suffix_array(text)
     lcp = oracle.kasai_lcp(text, sa)
@@ -96,7 +96,7 @@ def _ext_texts():
             ("AC_period2", b"AC" * 700 + b"A$")]
 
 
-@pytest.mark.parametrize("name,text", _ext_texts())
+@pytest.mark.parametrize("name,text", _ext_texts(), ids=[c[0] for c in _ext_texts()])
 def test_extend_and_consensus_batches(detect, oracle, name, text):
     rng = np.random.default_rng(len(text))
     n_total = len(text)

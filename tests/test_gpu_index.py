@@ -77,7 +77,7 @@ def _check_index(DeviceIndex, oracle, text: bytes, occ_rate=128, searches=True):
     return ix, oi
 
 
-@pytest.mark.parametrize("name,text", text_cases())
+@pytest.mark.parametrize("name,text", text_cases(), ids=[c[0] for c in text_cases()])
 def test_index_small_cases(DeviceIndex, oracle, name, text):
     _check_index(DeviceIndex, oracle, text)
 
@@ -99,6 +99,28 @@ def test_index_with_N_block_100k(DeviceIndex, oracle):
     s = gen_contig(100_000, 5)
     s[40_000:52_000] = ord("N")
     _check_index(DeviceIndex, oracle, s.tobytes() + b"$")
+
+
+def _refinement_cases():
+    """Texts that steer the doubling rounds through every sort path of sa.cu: whole groups in one
+    CTA window, deferred mid-size groups (one CTA each), groups too large for shared memory
+    (radix fallback), and mixtures of them next to ordinary sequence."""
+    rng = np.random.default_rng(123)
+    rnd = lambda n: bytes(b"ACGT"[x] for x in rng.integers(0, 4, n))
+    return [
+        ("allA_40000", b"A" * 40000 + b"$"),
+        ("allA_17000_no_sentinel", b"A" * 17000),
+        ("mid_runs", rnd(3000) + b"A" * 5000 + rnd(2000) + b"AC" * 3500 + rnd(1500) + b"ACG" * 2500 + rnd(4000)
+         + b"T" * 9000 + rnd(500) + b"$"),
+        ("huge_and_mid", rnd(2000) + b"N" * 30000 + rnd(3000) + b"GA" * 6000 + rnd(1000) + b"N" * 3000 + b"$"),
+        ("many_window_edges", b"".join(rnd(37) + b"CAGT" * int(k) for k in rng.integers(200, 400, 60)) + b"$"),
+        ("period_1300_copies", rnd(1300) * 40 + b"$"),
+    ]
+
+
+@pytest.mark.parametrize("name,text", _refinement_cases(), ids=[c[0] for c in _refinement_cases()])
+def test_index_refinement_paths(DeviceIndex, oracle, name, text):
+    _check_index(DeviceIndex, oracle, text, searches=False)
 
 
 def test_motif_sweep_matches_batched_search(DeviceIndex, oracle):
