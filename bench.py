@@ -216,30 +216,52 @@ def run_ours(args):
     sa_stats = step.stats.copy()
 
     # ---- e2e: host text in, SA + BWT + LCP out --------------------------------
-    h_sa = torch.empty(n, dtype=torch.int32).pin_memory()
-    h_bwt = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_lcp = torch.empty(n, dtype=torch.int32).pin_memory()
-    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
-    e2e_times = []
-    for it in range(args.warmup + args.steps):
+    # Through the package's public streaming API (bwt_algorithm_b200.streaming.IndexPipeline ->
+    # bwtk_index_build): every step uploads the contig from pinned host memory and downloads
+    # SA, BWT and LCP into pinned host buffers.  Two contigs are in flight (the multi-contig
+    # pipeline's steady state), so transfers of one overlap the kernels of the next; the serial
+    # one-contig-at-a-time figure is reported next to it.
+    from bwt_algorithm_b200.streaming import IndexPipeline
+    del step.ws
+    torch.cuda.empty_cache()
+    pipe = IndexPipeline(n, occ_rate=128, device=dev, slots=2, want_lcp=True)
+    h2d_b, d2h_b = pipe.bytes_per_contig(n)
+    for _ in range(max(args.warmup, 2)):
+        r = pipe.result(pipe.submit(pinned))
+    assert int(r["sa"][0]) == n - 1 and r["lcp"].shape[0] == n     # '$' sorts first
+    # serial: one contig at a time
+    serial = []
+    for _ in range(args.steps):
         flush.fill_(1)
-        barrier() if it == args.warmup else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        d_in.copy_(pinned, non_blocking=True)
-        step.run(d_in)
-        h_sa.copy_(step.sa, non_blocking=True)
-        h_bwt.copy_(step.bwt, non_blocking=True)
-        h_lcp.copy_(step.lcp, non_blocking=True)
-        e1.record()
         torch.cuda.synchronize()
-        if it >= args.warmup:
-            e2e_times.append(e0.elapsed_time(e1))
-    e2e_ms = float(sum(e2e_times))
+        t0 = time.perf_counter()
+        r = pipe.result(pipe.submit(pinned))
+        serial.append((time.perf_counter() - t0) * 1e3)
+    e2e_serial_ms = float(sum(serial))
+    # pipelined: K contigs back to back, timed with events from the first upload to the last download
+    pipe.drain()
+    torch.cuda.synchronize()
+    barrier()
+    first = pipe.slots[pipe.tickets % len(pipe.slots)]
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record(first.stream)
+    prev = None
+    for _ in range(args.steps):
+        tk = pipe.submit(pinned)
+        if prev is not None:
+            r = pipe.result(prev)
+            _ = int(r["sa"][0])       # the host consumes the previous contig while this one is in flight
+        prev = tk
+    r = pipe.result(prev)
+    pipe.drain()
+    e2e_ms = max(e0.elapsed_time(sl.done) for sl in pipe.slots)
     if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_ms, e2e_serial_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        e2e_ms, e2e_serial_ms = float(t[0].item()), float(t[1].item())
+    del pipe
+    torch.cuda.empty_cache()
+    step.ws = torch.empty(int(L.bwtk_index_workspace_bytes(n)), dtype=torch.uint8, device=dev)
 
     extras = {}
     roof = None
@@ -350,8 +372,12 @@ def run_ours(args):
             "config": {"workload": "chr21-sized planted contig per GPU (BASELINE configs[2])", "bases_per_gpu": args.n,
                        "generator": "SURVEY Appendix B gen_contig(seed=21+rank)", "occ_rate": 128,
                        "l2": "256 MB write between timed steps (flush)", "parallelism": f"contig-per-gpu x{world}"},
-            "e2e": {"value": round(e2e_val, 4), "unit": "Gbases/s", "h2d_bytes_per_step": n,
-                    "d2h_bytes_per_step": 9 * n, "ms_per_step": round(e2e_ms / args.steps, 4)},
+            "e2e": {"value": round(e2e_val, 4), "unit": "Gbases/s", "h2d_bytes_per_step": h2d_b,
+                    "d2h_bytes_per_step": d2h_b, "ms_per_step": round(e2e_ms / args.steps, 4),
+                    "in_flight": 2, "api": "bwt_algorithm_b200.streaming.IndexPipeline -> bwtk_index_build",
+                    "serial_ms_per_step": round(e2e_serial_ms / args.steps, 4),
+                    "serial_value": round(world * args.n * args.steps / (e2e_serial_ms * 1e-3) / 1e9, 4),
+                    "l2": "no flush between pipelined steps: each contig touches ~2 GB >> 126 MB L2"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -11,6 +11,11 @@ namespace bwtk {
 
 void set_error(const char *fmt, ...);
 void count_launch(int k = 1);
+// Zero-fill by a kernel.  cudaMemsetAsync may be served by a copy engine, where it queues behind the
+// bulk downloads of other streams (streaming.IndexPipeline) and stalls the build for milliseconds.
+cudaError_t zero_async(void *p, size_t bytes, cudaStream_t st);
+// dst <- bytes at d_src via mapped pinned memory (no copy engine); synchronises st
+int read_back(void *dst, const void *d_src, size_t bytes, cudaStream_t st);
 
 #define BWTK_CUDA(expr)                                                              \
     do {                                                                             \

@@ -817,7 +817,7 @@ extern "C" int32_t bwtk_extend_batch(const uint8_t *d_text, int64_t n, const int
     int64_t bytes = m * ext::scratch_per_thread(maxp) + 16;
     BWTK_CUDA(cudaMallocAsync((void **)&scratch, (size_t)bytes, st));
     d_err = (int *)(scratch + bytes - 16);
-    BWTK_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
+    BWTK_CUDA(bwtk::zero_async(d_err, 4, st));
     ext::extend_batch_kernel<<<(unsigned)ceil_div(m, 64), 64, 0, st>>>(d_text, n, d_seed, d_period, d_flags, m,
                                                                       mode, maxp, scratch, d_out, d_err);
     BWTK_LAUNCH_CHECK();
@@ -845,7 +845,7 @@ extern "C" int32_t bwtk_consensus_batch(const uint8_t *d_text, int64_t text_size
     int64_t bytes = m * ext::scratch_per_thread(maxp) + 16;
     BWTK_CUDA(cudaMallocAsync((void **)&scratch, (size_t)bytes, st));
     int *d_err = (int *)(scratch + bytes - 16);
-    BWTK_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
+    BWTK_CUDA(bwtk::zero_async(d_err, 4, st));
     ext::consensus_batch_kernel<<<(unsigned)ceil_div(m, 64), 64, 0, st>>>(
         d_text, text_size, d_start, d_period, d_copies, d_cons_off, m, maxp, scratch, d_cons, d_mm, d_err);
     BWTK_LAUNCH_CHECK();
@@ -922,8 +922,8 @@ extern "C" int32_t bwtk_period_scan(const uint8_t *d_text, int64_t n_total, int6
     unsigned long long *tmp_count = c.take<unsigned long long>(2);
     int64_t *d_iter = c.take<int64_t>(2);
     int *d_err = c.take<int>(4);
-    BWTK_CUDA(cudaMemsetAsync(tmp_count, 0, 16, st));
-    BWTK_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
+    BWTK_CUDA(bwtk::zero_async(tmp_count, 16, st));
+    BWTK_CUDA(bwtk::zero_async(d_err, 4, st));
     unsigned grid = (unsigned)npass;
     // run 1: visits per pass with an unlimited (MAX_ITER) budget each
     ext::period_pass_kernel<<<grid, ext::PASS_THREADS, 0, st>>>(cfg, npass, nullptr, visits, nullptr, nullptr, nullptr, 0,

@@ -24,6 +24,70 @@ void set_error(const char *fmt, ...)
 }
 void count_launch(int k) { g_launches += k; }
 
+// ---- small read-backs that bypass the copy engines --------------------------------
+// Control values (active counts, flags, the byte histogram) are read by the host several
+// times per build.  As cudaMemcpyAsync they queue on the device-to-host copy engine behind
+// whatever bulk download another stream has in flight (420 MB per chr21-sized contig in the
+// streaming pipeline) and stall the build for milliseconds.  Instead a one-warp kernel
+// stores them into mapped pinned host memory; the host reads it after the stream sync.
+namespace {
+constexpr size_t READ_BACK_MAX = 4096;
+__global__ void read_back_kernel(const unsigned char *__restrict__ src, unsigned char *dst, int bytes)
+{
+    for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+struct Staging {
+    unsigned char *host = nullptr;
+    ~Staging() { if (host) cudaFreeHost(host); }
+};
+}  // namespace
+
+namespace {
+__global__ void zero_kernel(unsigned char *p, size_t head, size_t vecs, size_t tail)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < head) p[t] = 0;
+    uint4 *v = reinterpret_cast<uint4 *>(p + head);
+    for (size_t i = t; i < vecs; i += stride) v[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (t < tail) p[head + vecs * 16 + t] = 0;
+}
+}  // namespace
+
+cudaError_t zero_async(void *p, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return cudaSuccess;
+    size_t head = (16 - ((uintptr_t)p & 15)) & 15;
+    if (head > bytes) head = bytes;
+    const size_t vecs = (bytes - head) / 16, tail = bytes - head - vecs * 16;
+    size_t want = (vecs + 255) / 256;
+    if (want < 1) want = 1;
+    if (want > (size_t)NUM_SMS * 8) want = (size_t)NUM_SMS * 8;
+    zero_kernel<<<(unsigned)want, 256, 0, st>>>((unsigned char *)p, head, vecs, tail);
+    count_launch();
+    return cudaGetLastError();
+}
+
+int read_back(void *dst, const void *d_src, size_t bytes, cudaStream_t st)
+{
+    static thread_local Staging stg;
+    if (bytes == 0) return BWTK_OK;
+    if (bytes > READ_BACK_MAX) {
+        BWTK_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+        BWTK_CUDA(cudaStreamSynchronize(st));
+        return BWTK_OK;
+    }
+    if (!stg.host)
+        BWTK_CUDA(cudaHostAlloc((void **)&stg.host, READ_BACK_MAX, cudaHostAllocPortable | cudaHostAllocMapped));
+    unsigned char *d_alias = nullptr;
+    BWTK_CUDA(cudaHostGetDevicePointer((void **)&d_alias, stg.host, 0));
+    read_back_kernel<<<1, 128, 0, st>>>((const unsigned char *)d_src, d_alias, (int)bytes);
+    BWTK_LAUNCH_CHECK();
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    memcpy(dst, stg.host, bytes);
+    return BWTK_OK;
+}
+
 namespace prof {
 struct Rec {
     const char *name;
@@ -104,7 +168,7 @@ __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restric
 int byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, int *h_last, unsigned long long *d_scratch,
                    cudaStream_t st)
 {
-    BWTK_CUDA(cudaMemsetAsync(d_scratch, 0, 257 * sizeof(unsigned long long), st));
+    BWTK_CUDA(bwtk::zero_async(d_scratch, 257 * sizeof(unsigned long long), st));
     if (n > 0) {
         int64_t want = ceil_div(n, 256 * 64);
         int grid = (int)(want < 1 ? 1 : (want > NUM_SMS * 8 ? NUM_SMS * 8 : want));
@@ -115,8 +179,10 @@ int byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals, int *h_l
         BWTK_LAUNCH_CHECK();
     }
     int64_t host[257];
-    BWTK_CUDA(cudaMemcpyAsync(host, d_scratch, 257 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaStreamSynchronize(st));
+    {
+        int rc = read_back(host, d_scratch, 257 * sizeof(int64_t), st);
+        if (rc) return rc;
+    }
     memcpy(h_totals, host, 256 * sizeof(int64_t));
     if (h_last) *h_last = (int)host[256];
     return BWTK_OK;
@@ -465,7 +531,59 @@ static int launch_lcp(const uint32_t *packed, const int32_t *d_sa, const uint32_
 
 using namespace bwtk;
 
-extern "C" int32_t bwtk_version(void) { return 101; }
+extern "C" int32_t bwtk_version(void) { return 102; }
+
+static __global__ void __launch_bounds__(256)
+    upload_kernel(const unsigned char *__restrict__ src, unsigned char *__restrict__ dst, size_t head, size_t vecs,
+                  size_t tail)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < head) dst[t] = src[t];
+    const uint4 *sv = reinterpret_cast<const uint4 *>(src + head);
+    uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+    for (size_t i = t; i < vecs; i += stride) dv[i] = sv[i];
+    if (t < tail) dst[head + vecs * 16 + t] = src[head + vecs * 16 + t];
+}
+
+extern "C" int32_t bwtk_download(const void *d_src, void *h_pinned, int64_t bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bytes <= 0) return BWTK_OK;
+    BWTK_REQUIRE(d_src && h_pinned, "null pointer");
+    cudaPointerAttributes at;
+    BWTK_CUDA(cudaPointerGetAttributes(&at, h_pinned));
+    BWTK_REQUIRE(at.type == cudaMemoryTypeHost && at.devicePointer, "destination must be pinned host memory");
+    unsigned char *dst = (unsigned char *)at.devicePointer;
+    BWTK_REQUIRE(((((uintptr_t)dst) | ((uintptr_t)d_src)) & 15) == 0, "pointers must be 16-byte aligned");
+    const size_t vecs = (size_t)bytes / 16, tail = (size_t)bytes - vecs * 16;
+    // few CTAs: PCIe is saturated long before the SMs are, and the next contig's kernels need them
+    upload_kernel<<<64, 256, 0, st>>>((const unsigned char *)d_src, dst, 0, vecs, tail);
+    BWTK_LAUNCH_CHECK();
+    return BWTK_OK;
+}
+
+extern "C" int32_t bwtk_upload_text(const uint8_t *h_pinned, uint8_t *d_dst, int64_t n, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return BWTK_OK;
+    BWTK_REQUIRE(h_pinned && d_dst, "null pointer");
+    cudaPointerAttributes at;
+    BWTK_CUDA(cudaPointerGetAttributes(&at, h_pinned));
+    BWTK_REQUIRE(at.type == cudaMemoryTypeHost && at.devicePointer, "source must be pinned host memory");
+    const unsigned char *src = (const unsigned char *)at.devicePointer;
+    size_t head = (16 - ((uintptr_t)src & 15)) & 15;
+    if (head > (size_t)n || (((uintptr_t)d_dst + head) & 15)) head = (size_t)n;   // misaligned pair: byte copy
+    size_t vecs = ((size_t)n - head) / 16, tail = (size_t)n - head - vecs * 16;
+    if (head == (size_t)n) {
+        // byte path through the vector loop is not possible; use the head/tail lanes in chunks
+        BWTK_CUDA(cudaMemcpyAsync(d_dst, h_pinned, (size_t)n, cudaMemcpyHostToDevice, st));
+        return BWTK_OK;
+    }
+    upload_kernel<<<NUM_SMS * 8, 256, 0, st>>>(src, d_dst, head, vecs, tail);
+    BWTK_LAUNCH_CHECK();
+    return BWTK_OK;
+}
 
 extern "C" int32_t bwtk_last_error(char *buf, int32_t buflen)
 {

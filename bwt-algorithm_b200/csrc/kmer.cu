@@ -101,7 +101,7 @@ extern "C" int32_t bwtk_kmer8_index(const uint8_t *d_text, int64_t n, int32_t *d
     cudaStream_t st = (cudaStream_t)stream;
     BWTK_REQUIRE(d_bucket_off && h_count, "null pointer");
     *h_count = 0;
-    BWTK_CUDA(cudaMemsetAsync(d_bucket_off, 0, 65537 * sizeof(int32_t), st));
+    BWTK_CUDA(bwtk::zero_async(d_bucket_off, 65537 * sizeof(int32_t), st));
     if (n < 8) { BWTK_CUDA(cudaStreamSynchronize(st)); return BWTK_OK; }
     BWTK_REQUIRE(d_text && d_pos && d_ws, "null pointer");
     BWTK_REQUIRE(n < (1ll << 30), "n must be < 2^30");
@@ -118,8 +118,8 @@ extern "C" int32_t bwtk_kmer8_index(const uint8_t *d_text, int64_t n, int32_t *d
     scan::Workspace sws = scan::carve(c, n);
     rsort::Workspace rws = rsort::carve(c, n);
     if (!c.ok()) { set_error("kmer8 workspace carve overflow"); return BWTK_EWORKSPACE; }
-    BWTK_CUDA(cudaMemsetAsync(sws.err, 0, sizeof(int), st));
-    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(sws.err, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(rws.err, sizeof(int), st));
 
     kmer::CountValid cv{d_text};
     kmer::EmitValid ev{d_text, cc, d_pos, vend};

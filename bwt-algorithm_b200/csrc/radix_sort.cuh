@@ -469,10 +469,10 @@ int sort_pairs_from(Source first, bool first_is_k0, KeyT *k0, uint32_t *v0, KeyT
         set_error("radix sort workspace too small (%lld tiles > %lld)", (long long)tiles, (long long)ws.max_tiles);
         return BWTK_EWORKSPACE;
     }
-    BWTK_CUDA(cudaMemsetAsync(ws.ghist, 0, MAX_PASSES * RADIX * 4, st));
-    BWTK_CUDA(cudaMemsetAsync(ws.counters, 0, MAX_PASSES * sizeof(unsigned), st));
+    BWTK_CUDA(bwtk::zero_async(ws.ghist, MAX_PASSES * RADIX * 4, st));
+    BWTK_CUDA(bwtk::zero_async(ws.counters, MAX_PASSES * sizeof(unsigned), st));
     // status words of pass p live at ws.status + p*max_tiles*RADIX; only `tiles` of them are used
-    BWTK_CUDA(cudaMemsetAsync(ws.status, 0, (size_t)((plan.passes - 1) * ws.max_tiles + tiles) * RADIX * 4, st));
+    BWTK_CUDA(bwtk::zero_async(ws.status, (size_t)((plan.passes - 1) * ws.max_tiles + tiles) * RADIX * 4, st));
     int hgrid = (int)(ceil_div(n, 512 * 16) < NUM_SMS * 4 ? ceil_div(n, 512 * 16) : NUM_SMS * 4);
     if (hgrid < 1) hgrid = 1;
     bool hist_done = false;

@@ -500,8 +500,8 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
         return BWTK_EWORKSPACE;
     }
     if (n == 1) {
-        BWTK_CUDA(cudaMemsetAsync(d_sa, 0, 4, st));
-        if (d_isa_out) BWTK_CUDA(cudaMemsetAsync(d_isa_out, 0, 4, st));
+        BWTK_CUDA(bwtk::zero_async(d_sa, 4, st));
+        if (d_isa_out) BWTK_CUDA(bwtk::zero_async(d_isa_out, 4, st));
         BWTK_CUDA(cudaStreamSynchronize(st));
         if (h_stats) { h_stats[0] = 1; h_stats[1] = bits; h_stats[2] = 32 / bits; h_stats[6] = fast ? 1 : 0; }
         return BWTK_OK;
@@ -530,9 +530,9 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     unsigned *d_counts = counters + 1;
     const int S = 32 / bits;
 
-    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
-    BWTK_CUDA(cudaMemsetAsync(counters, 0, (sa::MAX_ROUNDS + 8) * sizeof(unsigned), st));
-    BWTK_CUDA(cudaMemsetAsync(abits, 0, (size_t)(n / 32 + 2) * 4, st));
+    BWTK_CUDA(bwtk::zero_async(rws.err, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(counters, (sa::MAX_ROUNDS + 8) * sizeof(unsigned), st));
+    BWTK_CUDA(bwtk::zero_async(abits, (size_t)(n / 32 + 2) * 4, st));
     int64_t passes = 0;
     int in_first = 1;
     // round-0 ping-pong buffers chosen so that the sorted keys land in `skeep`
@@ -556,7 +556,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     uint32_t *suf_other = in_first ? val1 : val0;  // free value buffer receives the active suffixes
     {
         int64_t tiles = ceil_div(n, sa::RG_TILE);
-        BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
+        BWTK_CUDA(bwtk::zero_async(rg_status, (size_t)tiles * 8, st));
         {
             prof::Scope ps("regroup_first", n * 16, st);
             sa::regroup_kernel<uint32_t, true><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
@@ -566,8 +566,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
         BWTK_LAUNCH_CHECK();
     }
     unsigned h_count = 0;
-    BWTK_CUDA(cudaMemcpyAsync(&h_count, d_counts + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaStreamSynchronize(st));
+    { int rc = read_back(&h_count, d_counts + 1, sizeof(unsigned), st); if (rc) return rc; }
     const int64_t active0 = h_count;
     // after round 0 the active list lives in (pos_out, suf_other, grp)
     uint32_t *suf_in = suf_other;
@@ -587,8 +586,8 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     while (true) {
         const unsigned *d_m = d_counts + round;
         if (round > 1) {   // round 1's count was read after the first regroup
-            BWTK_CUDA(cudaMemcpyAsync(&h_count, d_m, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            BWTK_CUDA(cudaStreamSynchronize(st));
+            int rc = read_back(&h_count, d_m, sizeof(unsigned), st);
+            if (rc) return rc;
         }
         if (h_count == 0) break;
         if (round >= sa::MAX_ROUNDS || h > 4 * n) {
@@ -602,7 +601,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
         const bool seg = bound <= sa::SEG_MAX;
         unsigned h_ctl[2] = {0, 1};   // [1] != 0: use the radix path
         if (seg) {
-            BWTK_CUDA(cudaMemsetAsync(ctl, 0, 8, st));
+            BWTK_CUDA(bwtk::zero_async(ctl, 8, st));
             uint32_t *k2buf = reinterpret_cast<uint32_t *>(keyA);   // keyA is only used by the radix path
             {
                 prof::Scope ps("build_k2_kernel", bound * 12, st);
@@ -621,8 +620,8 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
                                                                            ctl);
             }
             BWTK_LAUNCH_CHECK();
-            BWTK_CUDA(cudaMemcpyAsync(h_ctl, ctl, 8, cudaMemcpyDeviceToHost, st));
-            BWTK_CUDA(cudaStreamSynchronize(st));
+            int rc = read_back(h_ctl, ctl, 8, st);
+            if (rc) return rc;
         }
         uint64_t *sk = keyB;
         uint32_t *ss = suf_free, *sn = suf_in;
@@ -642,8 +641,8 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
             sn = in_first ? suf_free : suf_in;  // the other value buffer takes the next list
         }
         int64_t tiles = ceil_div((int64_t)h_count, sa::RG_TILE);
-        BWTK_CUDA(cudaMemsetAsync(rg_status, 0, (size_t)tiles * 8, st));
-        BWTK_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned), st));
+        BWTK_CUDA(bwtk::zero_async(rg_status, (size_t)tiles * 8, st));
+        BWTK_CUDA(bwtk::zero_async(counters, sizeof(unsigned), st));
         {
             prof::Scope ps("regroup_round", (int64_t)h_count * 36, st);
             sa::regroup_kernel<uint64_t, false><<<(unsigned)tiles, sa::RG_THREADS, 0, st>>>(
@@ -664,9 +663,8 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     }
     int h_err = 0;
     unsigned h_counts[sa::MAX_ROUNDS + 1];
-    BWTK_CUDA(cudaMemcpyAsync(&h_err, rws.err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaStreamSynchronize(st));
+    { int rc = read_back(&h_err, rws.err, sizeof(int), st); if (rc) return rc; }
+    { int rc = read_back(h_counts, d_counts, sizeof(h_counts), st); if (rc) return rc; }
     if (h_err) {
         set_error("look-back spin limit hit (code %d)", h_err);
         return BWTK_EINTERNAL;

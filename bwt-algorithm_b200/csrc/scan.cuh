@@ -134,11 +134,11 @@ __global__ void __launch_bounds__(THREADS)
 template <typename Count, typename Emit>
 int run(int64_t n, Count count, Emit emit, const Workspace &ws, cudaStream_t st)
 {
-    BWTK_CUDA(cudaMemsetAsync(ws.total, 0, 8, st));
+    BWTK_CUDA(bwtk::zero_async(ws.total, 8, st));
     if (n <= 0) return BWTK_OK;
     int64_t tiles = tiles_for(n);
-    BWTK_CUDA(cudaMemsetAsync(ws.status, 0, (size_t)tiles * 8, st));
-    BWTK_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(unsigned), st));
+    BWTK_CUDA(bwtk::zero_async(ws.status, (size_t)tiles * 8, st));
+    BWTK_CUDA(bwtk::zero_async(ws.counter, sizeof(unsigned), st));
     scan_kernel<Count, Emit><<<(unsigned)tiles, THREADS, 0, st>>>(n, count, emit, ws.status, ws.counter,
                                                                  ws.total, ws.err);
     BWTK_LAUNCH_CHECK();

@@ -524,7 +524,7 @@ static int greedy_pass(int64_t npos, int64_t limit, int64_t step, int abits, Can
     }
     coarse_walk_kernel<<<1, 32, 0, st>>>(jbig, w.d_first, w.anchor, w.d_nanchor);
     BWTK_LAUNCH_CHECK();
-    BWTK_CUDA(cudaMemsetAsync(w.onpath, 0, (size_t)K, st));
+    BWTK_CUDA(bwtk::zero_async(w.onpath, (size_t)K, st));
     int64_t max_anchor = (K >> kappa) + 2;
     fine_walk_kernel<<<(unsigned)ceil_div(max_anchor, 128), 128, 0, st>>>(w.succ, w.anchor, w.d_nanchor,
                                                                         1ll << kappa, w.onpath);
@@ -719,8 +719,8 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
         Carver cg(d_ws, ws_bytes);
         tier1::PassWs pw = tier1::carve_pass_ws(cg, n_total);
         if (!cg.ok()) { set_error("strict workspace carve overflow"); return BWTK_EWORKSPACE; }
-        BWTK_CUDA(cudaMemsetAsync(pw.rws.err, 0, sizeof(int), st));
-        BWTK_CUDA(cudaMemsetAsync(pw.sws.err, 0, sizeof(int), st));
+        BWTK_CUDA(bwtk::zero_async(pw.rws.err, sizeof(int), st));
+        BWTK_CUDA(bwtk::zero_async(pw.sws.err, sizeof(int), st));
         const int abits_g = strict::bits_for(n);
         int64_t total = 0;
         for (int64_t u = umax; u >= min_unit_len; u--) {
@@ -757,9 +757,9 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
     scan::Workspace sws = scan::carve(c, ccap);
     unsigned long long *d_count = c.take<unsigned long long>(2);
     if (!c.ok()) { set_error("strict workspace carve overflow"); return BWTK_EWORKSPACE; }
-    BWTK_CUDA(cudaMemsetAsync(d_count, 0, 16, st));
-    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
-    BWTK_CUDA(cudaMemsetAsync(sws.err, 0, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(d_count, 16, st));
+    BWTK_CUDA(bwtk::zero_async(rws.err, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(sws.err, sizeof(int), st));
 
     strict::CandOut out;
     out.key = key0; out.val = val0; out.count = d_count; out.cap = ccap;
@@ -865,9 +865,9 @@ extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max
     tier1::PassWs pw = tier1::carve_pass_ws(c, n);
     double *d_plogp = c.take<double>(100);
     if (!c.ok()) { set_error("tier1 workspace carve overflow"); return BWTK_EWORKSPACE; }
-    BWTK_CUDA(cudaMemsetAsync(seen, 0, (size_t)n, st));
-    BWTK_CUDA(cudaMemsetAsync(pw.rws.err, 0, sizeof(int), st));
-    BWTK_CUDA(cudaMemsetAsync(pw.sws.err, 0, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(seen, (size_t)n, st));
+    BWTK_CUDA(bwtk::zero_async(pw.rws.err, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(pw.sws.err, sizeof(int), st));
     // (c/L)*log2(c/L) in IEEE double, the same expression the host evaluates
     double plogp[100];
     for (int L = 0; L < 10; L++)
@@ -945,9 +945,9 @@ extern "C" int32_t bwtk_lcp_plateaus(const uint8_t *d_text, int64_t n_text, cons
     scan::Workspace sws = scan::carve(c, n);
     int *d_max = c.take<int>(4);
     if (!c.ok()) { set_error("plateau workspace carve overflow"); return BWTK_EWORKSPACE; }
-    BWTK_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), st));
-    BWTK_CUDA(cudaMemsetAsync(rws.err, 0, sizeof(int), st));
-    BWTK_CUDA(cudaMemsetAsync(sws.err, 0, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(d_max, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(rws.err, sizeof(int), st));
+    BWTK_CUDA(bwtk::zero_async(sws.err, sizeof(int), st));
     int grid = (int)(ceil_div(n, 256 * 8) < NUM_SMS * 8 ? ceil_div(n, 256 * 8) : NUM_SMS * 8);
     plateau::max_kernel<<<grid, 256, 0, st>>>(d_lcp, n, d_max);
     BWTK_LAUNCH_CHECK();

@@ -53,6 +53,17 @@ int64_t bwtk_launch_count(void);
 int32_t bwtk_profile_enable(int32_t on);
 int32_t bwtk_profile_report(char *buf, int32_t buflen);
 
+/* ---- text ingest: BWTCore.__init__'s text_arr (bwt.py:122) ---------------
+ * Copies n bytes from PINNED host memory (cudaHostAlloc / torch pin_memory,
+ * device-accessible under unified addressing) to d_dst with a kernel instead of
+ * a copy engine, so that the upload of one contig is never queued behind the
+ * bulk downloads of another stream (streaming.IndexPipeline).  Asynchronous. */
+int32_t bwtk_upload_text(const uint8_t *h_pinned, uint8_t *d_dst, int64_t n, void *stream);
+/* The other direction (suffix_array / bwt_arr / LCP as host arrays, bwt.py:127-128, 55-72):
+ * `bytes` from device memory into PINNED host memory by a kernel that stores straight
+ * over PCIe, for the same reason.  Both pointers 16-byte aligned.  Asynchronous. */
+int32_t bwtk_download(const void *d_src, void *h_pinned, int64_t bytes, void *stream);
+
 /* ---- a5: BWTCore._build_char_counts (bwt.py:276-286) ------------------
  * byte histogram of the text; h_totals[256] (host) receives the counts.
  * The exclusive prefix sum over present bytes (the FM "C" array) is a 256-entry

@@ -202,3 +202,58 @@ def test_standalone_entry_points(oracle):
         ws3 = torch.empty(int(L.bwtk_lcp_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
         _lib.check(L.bwtk_lcp_build(d.data_ptr(), sa.data_ptr(), n, lcp.data_ptr(), ws3.data_ptr(), ws3.numel(), st), "lcp")
         assert np.array_equal(lcp.cpu().numpy(), oi.lcp())
+
+
+def test_index_pipeline_overlapped_builds(DeviceIndex, oracle):
+    """streaming.IndexPipeline: several contigs in flight, results identical to one-at-a-time builds."""
+    import torch
+
+    from bwt_algorithm_b200 import _lib
+    from bwt_algorithm_b200.streaming import IndexPipeline
+
+    texts = [gen_contig(n, 60 + i).tobytes() + b"$" for i, n in enumerate((90_000, 30_000, 120_000, 5, 64_000))]
+    pipe = IndexPipeline(max(len(t) for t in texts), slots=2)
+    tickets = []
+    results = {}
+    for i, t in enumerate(texts):
+        host = torch.from_numpy(np.frombuffer(t, np.uint8).copy()).pin_memory()
+        tickets.append(pipe.submit(host))
+        if i >= 1:   # consume the previous one while this one is in flight
+            r = pipe.result(tickets[i - 1])
+            results[i - 1] = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items() if k != "occ"}
+    r = pipe.result(tickets[-1])
+    results[len(texts) - 1] = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items() if k != "occ"}
+    for i, t in enumerate(texts):
+        oi = oracle.OracleIndex(t)
+        assert results[i]["n"] == len(t)
+        assert np.array_equal(results[i]["sa"], oi.sa), f"contig {i}: SA"
+        assert np.array_equal(results[i]["bwt"], oi.bwt), f"contig {i}: BWT"
+        assert np.array_equal(results[i]["lcp"], oi.lcp()), f"contig {i}: LCP"
+        assert np.array_equal(results[i]["totals"], oi.totals)
+    with pytest.raises(_lib.BwtkError):
+        pipe.result(tickets[0])            # slot reused
+    with pytest.raises(_lib.BwtkError):
+        pipe.submit(np.zeros(10 ** 6, np.uint8))   # larger than max_n
+
+
+def test_kernel_transfers_roundtrip():
+    """bwtk_upload_text / bwtk_download: pinned host <-> device without a copy engine."""
+    import torch
+
+    from bwt_algorithm_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    for n in (1, 15, 16, 4097, 1_000_003):
+        host = torch.from_numpy(rng.integers(0, 256, n, dtype=np.uint8)).pin_memory()
+        dev = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        _lib.check(L.bwtk_upload_text(host.data_ptr(), dev.data_ptr(), n, _lib.stream_ptr()), "upload")
+        torch.cuda.synchronize()
+        assert torch.equal(dev.cpu(), host)
+        back = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        _lib.check(L.bwtk_download(dev.data_ptr(), back.data_ptr(), n, _lib.stream_ptr()), "download")
+        torch.cuda.synchronize()
+        assert torch.equal(back, host)
+    pageable = torch.zeros(64, dtype=torch.uint8)
+    dev = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    assert L.bwtk_upload_text(pageable.data_ptr(), dev.data_ptr(), 64, _lib.stream_ptr()) != 0   # not pinned
