@@ -1,5 +1,7 @@
+"""Per-contig timeline of the two-slot index pipeline (upload, build, download) from CUDA events:
+shows which builds overlap the other slot's download."""
 import sys, time, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bwt_algorithm_b200
 from bench import gen_contig
 from bwt_algorithm_b200 import _lib
@@ -21,7 +23,7 @@ for i in range(4):
     E = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     with torch.cuda.stream(slot.stream):
         E[0].record()
-        L.bwtk_upload_text(pinned.data_ptr(), slot.d_text.data_ptr(), n, slot.stream.cuda_stream)
+        slot.d_text.copy_(pinned, non_blocking=True)
         E[1].record()
         h0 = time.perf_counter()
         rc = L.bwtk_index_build(slot.d_text.data_ptr(), n, 128, slot.sa.data_ptr(), None, slot.bwt.data_ptr(), slot.occ.data_ptr(), 8,
