@@ -40,6 +40,7 @@ class _Slot:
         self.stats = np.zeros(8, np.int64)
         self.start = torch.cuda.Event(enable_timing=True)
         self.done = torch.cuda.Event(enable_timing=True)
+        self.built = torch.cuda.Event()
         self.n = 0
         self.busy = False
 
@@ -60,6 +61,8 @@ class IndexPipeline:
             self.slots: List[_Slot] = [_Slot(torch, self.L, self.max_n, self.occ_rate, self.device, want_lcp)
                                        for _ in range(max(1, int(slots)))]
         self.tickets = 0
+        with torch.cuda.device(self.device):
+            self.dl_stream = torch.cuda.Stream(device=self.device)
         self.kernel_copies = False   # True: transfers by SM kernels (bwtk_upload_text / bwtk_download)
 
     def submit(self, host_text) -> int:
@@ -88,11 +91,18 @@ class IndexPipeline:
                                     slot.totals.ctypes.data, slot.row.ctypes.data, slot.stats.ctypes.data,
                                     slot.ws.data_ptr(), slot.ws.numel(), slot.stream.cuda_stream)
             _lib.check(rc, "index_build")
+            slot.built.record()
+        # All downloads go through ONE stream, in order.  A download enqueued on its own stream
+        # while another stream's download occupies the copy engine gets parked in hardware, and
+        # every kernel submitted afterwards -- the next contig's build -- waits for it (measured:
+        # every second build started 7 ms late).  Stream order keeps the queue in software.
+        with torch.cuda.device(self.device), torch.cuda.stream(self.dl_stream):
+            self.dl_stream.wait_event(slot.built)
             if self.kernel_copies:
                 for dst, src in ((slot.h_sa, slot.sa), (slot.h_bwt, slot.bwt), (slot.h_lcp, slot.lcp)):
                     if src is not None:
                         _lib.check(L.bwtk_download(src.data_ptr(), dst.data_ptr(), n * src.element_size(),
-                                                   slot.stream.cuda_stream), "download")
+                                                   self.dl_stream.cuda_stream), "download")
             else:
                 slot.h_sa[:n].copy_(slot.sa[:n], non_blocking=True)
                 slot.h_bwt[:n].copy_(slot.bwt[:n], non_blocking=True)
