@@ -77,48 +77,40 @@ __global__ void __launch_bounds__(THREADS)
     uint32_t base[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) base[c] = s32[(warp * 1024 + c * 128 + 4 * lane) >> 2];
-    // Unit lengths in aligned blocks of four: every tile offset is a multiple of 4, so the
-    // windows of u = 4k..4k+3 come out of the same two shared-memory words by funnel shifts
-    // (one LDS.64-worth of traffic per four compares instead of per compare).
-    for (int64_t ublk = ua & ~(int64_t)3; ublk <= ub; ublk += 4) {
+    for (int64_t u = ua; u <= ub; u++) {
+        const int64_t L = (mc - 1) * u;
+        const int64_t lim = n - u;  // E_u[j] defined for j < lim
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             const int loc = warp * 1024 + c * 128 + 4 * lane;
-            const int w = (loc + (int)ublk) >> 2;
-            const uint32_t a = s32[w], b = s32[w + 1];
+            const int off = loc + (int)u;
+            uint32_t a = s32[off >> 2], b = s32[(off >> 2) + 1];
+            uint32_t sh = __funnelshift_r(a, b, (off & 3) * 8);
             const int64_t pos = t0 + loc;
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int64_t u = ublk + r;
-                if (u < ua || u > ub) continue;
-                const int64_t L = (mc - 1) * u;
-                const int64_t lim = n - u;  // E_u[j] defined for j < lim
-                const uint32_t sh = r ? __funnelshift_r(a, b, r * 8) : a;
-                bool ok = (sh == base[c]) && (pos + 3 < lim);
-                unsigned B = __ballot_sync(0xffffffffu, ok);
-                if (B == 0) continue;
-                bool prev_ok = __shfl_up_sync(0xffffffffu, ok, 1);
-                if (lane == 0) {
-                    prev_ok = false;
-                    if (pos >= 4) {
-                        prev_ok = true;
-                        for (int q = 1; q <= 4; q++)
-                            if (__ldg(text + pos - q) != __ldg(text + pos - q + u)) { prev_ok = false; break; }
-                    }
+            bool ok = (sh == base[c]) && (pos + 3 < lim);
+            unsigned B = __ballot_sync(0xffffffffu, ok);
+            if (B == 0) continue;
+            bool prev_ok = __shfl_up_sync(0xffffffffu, ok, 1);
+            if (lane == 0) {
+                prev_ok = false;
+                if (pos >= 4) {
+                    prev_ok = true;
+                    for (int q = 1; q <= 4; q++)
+                        if (__ldg(text + pos - q) != __ldg(text + pos - q + u)) { prev_ok = false; break; }
                 }
-                if (ok && !prev_ok) {
-                    // streak of full groups starting at this lane
-                    unsigned rest = ~(B >> lane);
-                    int g = rest ? (__ffs(rest) - 1) : 32;
-                    if (g > 32 - lane) g = 32 - lane;
-                    bool ends_here = (lane + g) < 32;
-                    if (!ends_here || (int64_t)4 * g + 6 >= L) {
-                        int64_t ra = pos;
-                        while (ra > 0 && __ldg(text + ra - 1) == __ldg(text + ra - 1 + u)) ra--;
-                        int64_t rb = pos + 4 * g;
-                        while (rb < lim && __ldg(text + rb) == __ldg(text + rb + u)) rb++;
-                        if (rb - ra >= L) push_cand(out, u, ra, rb);
-                    }
+            }
+            if (ok && !prev_ok) {
+                // streak of full groups starting at this lane
+                unsigned rest = ~(B >> lane);
+                int g = rest ? (__ffs(rest) - 1) : 32;
+                if (g > 32 - lane) g = 32 - lane;
+                bool ends_here = (lane + g) < 32;
+                if (!ends_here || (int64_t)4 * g + 6 >= L) {
+                    int64_t ra = pos;
+                    while (ra > 0 && __ldg(text + ra - 1) == __ldg(text + ra - 1 + u)) ra--;
+                    int64_t rb = pos + 4 * g;
+                    while (rb < lim && __ldg(text + rb) == __ldg(text + rb + u)) rb++;
+                    if (rb - ra >= L) push_cand(out, u, ra, rb);
                 }
             }
         }
