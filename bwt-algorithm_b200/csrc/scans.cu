@@ -45,6 +45,65 @@ __device__ __forceinline__ void push_cand(const CandOut &o, int64_t u, int64_t a
     }
 }
 
+// A warp step found matching groups: extend every streak that can still reach the minimum run
+// length to its maximal run and push it.  Kept out of line so that the hot loop stays small.
+__device__ __noinline__ void run_candidates(const uint8_t *__restrict__ text, int64_t n, int u, int64_t L,
+                                            int64_t pos, bool ok, unsigned B, const CandOut &out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t lim = n - u;  // E_u[j] defined for j < lim
+    bool prev_ok = __shfl_up_sync(0xffffffffu, ok, 1);
+    if (lane == 0) {
+        prev_ok = false;
+        if (pos >= 4) {
+            prev_ok = true;
+            for (int q = 1; q <= 4; q++)
+                if (__ldg(text + pos - q) != __ldg(text + pos - q + u)) { prev_ok = false; break; }
+        }
+    }
+    if (ok && !prev_ok) {
+        // streak of full groups starting at this lane
+        unsigned rest = ~(B >> lane);
+        int g = rest ? (__ffs(rest) - 1) : 32;
+        if (g > 32 - lane) g = 32 - lane;
+        bool ends_here = (lane + g) < 32;
+        if (!ends_here || (int64_t)4 * g + 6 >= L) {
+            int64_t ra = pos;
+            while (ra > 0 && __ldg(text + ra - 1) == __ldg(text + ra - 1 + u)) ra--;
+            int64_t rb = pos + 4 * g;
+            while (rb < lim && __ldg(text + rb) == __ldg(text + rb + u)) rb++;
+            if (rb - ra >= L) push_cand(out, u, ra, rb);
+        }
+    }
+}
+
+// Unit lengths [u_from, u_to] of one tile.  INTERIOR: every group of the tile lies before
+// n - u - 3, no bounds test.  PAIRS: a run of >= 11 matches contains two adjacent aligned groups
+// of 4 (or reaches the next chunk through lane 31), so single matching groups -- one warp step
+// in eight on random sequence -- are not looked at.
+template <bool INTERIOR, bool PAIRS>
+__device__ __forceinline__ void scan_units(const uint8_t *__restrict__ text, int64_t n, int64_t t0, int u_from,
+                                           int u_to, int mc, const uint32_t *wbase, const uint32_t (&base)[8],
+                                           const CandOut &out)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int local = warp * 1024 + 4 * lane;
+    for (int u = u_from; u <= u_to; u++) {
+        const uint32_t *p = wbase + (u >> 2);
+        const int sh = (u & 3) * 8;
+        const int last_ok = INTERIOR ? 0 : (int)((n - u - 3 - t0 < (int64_t)TP + 8) ? (n - u - 3 - t0) : (int64_t)TP + 8);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint32_t w = __funnelshift_r(p[c * 32], p[c * 32 + 1], sh);
+            bool ok = w == base[c];
+            if (!INTERIOR) ok = ok && (local + c * 128 < last_ok);
+            const unsigned B = __ballot_sync(0xffffffffu, ok);
+            if (PAIRS ? ((B & (B >> 1)) == 0u && (int)B >= 0) : (B == 0u)) continue;
+            run_candidates(text, n, u, (int64_t)(mc - 1) * u, t0 + local + c * 128, ok, B, out);
+        }
+    }
+}
+
 // Units whose minimum run (mc-1)*u is >= 8 positions: a qualifying run then
 // contains at least one aligned group of 4 matching positions, so one 4-byte
 // compare per lane + a ballot filters 128 positions per warp step.
@@ -77,43 +136,17 @@ __global__ void __launch_bounds__(THREADS)
     uint32_t base[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) base[c] = s32[(warp * 1024 + c * 128 + 4 * lane) >> 2];
-    for (int64_t u = ua; u <= ub; u++) {
-        const int64_t L = (mc - 1) * u;
-        const int64_t lim = n - u;  // E_u[j] defined for j < lim
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const int loc = warp * 1024 + c * 128 + 4 * lane;
-            const int off = loc + (int)u;
-            uint32_t a = s32[off >> 2], b = s32[(off >> 2) + 1];
-            uint32_t sh = __funnelshift_r(a, b, (off & 3) * 8);
-            const int64_t pos = t0 + loc;
-            bool ok = (sh == base[c]) && (pos + 3 < lim);
-            unsigned B = __ballot_sync(0xffffffffu, ok);
-            if (B == 0) continue;
-            bool prev_ok = __shfl_up_sync(0xffffffffu, ok, 1);
-            if (lane == 0) {
-                prev_ok = false;
-                if (pos >= 4) {
-                    prev_ok = true;
-                    for (int q = 1; q <= 4; q++)
-                        if (__ldg(text + pos - q) != __ldg(text + pos - q + u)) { prev_ok = false; break; }
-                }
-            }
-            if (ok && !prev_ok) {
-                // streak of full groups starting at this lane
-                unsigned rest = ~(B >> lane);
-                int g = rest ? (__ffs(rest) - 1) : 32;
-                if (g > 32 - lane) g = 32 - lane;
-                bool ends_here = (lane + g) < 32;
-                if (!ends_here || (int64_t)4 * g + 6 >= L) {
-                    int64_t ra = pos;
-                    while (ra > 0 && __ldg(text + ra - 1) == __ldg(text + ra - 1 + u)) ra--;
-                    int64_t rb = pos + 4 * g;
-                    while (rb < lim && __ldg(text + rb) == __ldg(text + rb + u)) rb++;
-                    if (rb - ra >= L) push_cand(out, u, ra, rb);
-                }
-            }
-        }
+    const uint32_t *wbase = s32 + warp * 256 + lane;   // word of this lane's group in chunk 0
+    // first unit length whose minimum run (mc-1)*u reaches 11
+    int64_t u_pairs = (10 + (mc - 1)) / (mc - 1);
+    if (u_pairs < ua) u_pairs = ua;
+    if (u_pairs > ub + 1) u_pairs = ub + 1;
+    if (t0 + TP + 3 + ub < n) {
+        scan_units<true, false>(text, n, t0, (int)ua, (int)u_pairs - 1, (int)mc, wbase, base, out);
+        scan_units<true, true>(text, n, t0, (int)u_pairs, (int)ub, (int)mc, wbase, base, out);
+    } else {
+        scan_units<false, false>(text, n, t0, (int)ua, (int)u_pairs - 1, (int)mc, wbase, base, out);
+        scan_units<false, true>(text, n, t0, (int)u_pairs, (int)ub, (int)mc, wbase, base, out);
     }
 }
 
