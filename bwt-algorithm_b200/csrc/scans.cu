@@ -255,6 +255,61 @@ static int bits_for(int64_t v)
 
 static int64_t cand_capacity(int64_t n) { return n / 2 + 65536; }
 
+// All maximal runs of text[j]==text[j+u], u in [u_lo, u_hi], at least (mc-1)*u long, sorted by
+// (u descending, start): *sk / *sv (run start in the low `abits` key bits, run end), *m runs.
+// Returns BWTK_EWORKSPACE when more than `ccap` runs exist (*m then holds the count).
+static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t u_hi, int64_t mc,
+                        unsigned long long *key0, unsigned long long *key1, uint32_t *val0, uint32_t *val1,
+                        unsigned long long *d_count, int64_t ccap, const rsort::Workspace &rws, cudaStream_t st,
+                        const unsigned long long **sk, const uint32_t **sv, int64_t *m)
+{
+    *m = 0;
+    BWTK_CUDA(bwtk::zero_async(d_count, 16, st));
+    CandOut out;
+    out.key = key0; out.val = val0; out.count = d_count; out.cap = ccap;
+    out.abits = bits_for(n); out.umax = u_hi;
+    // units with (mc-1)*u < 8 take the per-position kernel, the rest the ballot kernel
+    int64_t small_hi = 7 / (mc - 1);
+    if (small_hi > u_hi) small_hi = u_hi;
+    if (small_hi >= u_lo) {
+        find_runs_small_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_text, n, u_lo, small_hi, mc, out);
+        BWTK_LAUNCH_CHECK();
+    }
+    int64_t big_lo = small_hi + 1 > u_lo ? small_hi + 1 : u_lo;
+    if (big_lo <= u_hi) {
+        int64_t tiles = ceil_div(n, TP);
+        int64_t nu = u_hi - big_lo + 1;
+        // enough CTAs to fill the machine even for short contigs
+        int64_t ysplit = ceil_div((int64_t)NUM_SMS * 8, tiles);
+        if (ysplit > nu) ysplit = nu;
+        if (ysplit < 1) ysplit = 1;
+        if (ysplit > 65535) ysplit = 65535;
+        int64_t u_per_block = ceil_div(nu, ysplit);
+        ysplit = ceil_div(nu, u_per_block);
+        size_t smem = (size_t)(TP + u_hi + 16);
+        static size_t smem_set = 0;
+        if (smem > 48 * 1024 && smem > smem_set) {
+            BWTK_CUDA(cudaFuncSetAttribute(find_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+        dim3 grid((unsigned)tiles, (unsigned)ysplit);
+        find_runs_kernel<<<grid, THREADS, smem, st>>>(d_text, n, big_lo, u_hi, u_per_block, mc, out);
+        BWTK_LAUNCH_CHECK();
+    }
+    unsigned long long h_cand = 0;
+    { int rc = read_back(&h_cand, d_count, 8, st); if (rc) return rc; }
+    *m = (int64_t)h_cand;
+    if ((int64_t)h_cand > ccap) return BWTK_EWORKSPACE;
+    if (h_cand == 0) return BWTK_OK;
+    int in_first = 1;
+    int rc = rsort::sort_pairs<unsigned long long>(key0, val0, key1, val1, (int64_t)h_cand, 0,
+                                                   out.abits + bits_for(u_hi), rws, st, &in_first, nullptr);
+    if (rc) return rc;
+    *sk = in_first ? key0 : key1;
+    *sv = in_first ? val0 : val1;
+    return BWTK_OK;
+}
+
 }  // namespace strict
 
 // ===========================================================================
@@ -334,6 +389,114 @@ struct Tier1Cand {
     struct State { int64_t mis = -1; };
     __device__ int64_t operator()(int64_t i, State &st) const { return would_emit(p, i, st.mis); }
 };
+
+// ---- candidates from maximal runs ----------------------------------------------
+// Position i is a Tier 1 candidate of motif length m iff the run of text[j]==text[j+m] from i
+// is at least (mc-1)*m long, i.e. iff i lies in a maximal run [ra, rb) found by
+// strict::find_runs_* with rb - i >= (mc-1)*m.  The runs of all motif lengths come from one
+// launch over the text; a pass then only expands its own runs (a few percent of the
+// positions) instead of testing every position.  The remaining tests are would_emit's.
+struct RunCand {
+    Params p;
+    const unsigned long long *rkey;   // runs of this motif length, sorted by start (low abits)
+    const uint32_t *rend;
+    int abits;
+    // calls sink(i, array_end) for the candidates of run r in ascending order; returns their number
+    template <typename Sink> __device__ int64_t visit(int64_t r, Sink &sink) const
+    {
+        const int m = p.m;
+        const uint8_t *t = p.text;
+        const int64_t ra = (int64_t)(rkey[r] & ((1ull << abits) - 1ull)), rb = (int64_t)rend[r];
+        // the run region has period m: a non-ACGT symbol among its first m is in every window
+        for (int q = 0; q < m; q++)
+            if (!acgt(__ldg(t + ra + q))) return 0;
+        const int64_t need = (int64_t)(p.mc - 1) * m;
+        int64_t hi = rb - need;
+        if (hi > p.n - m - 1) hi = p.n - m - 1;
+        int64_t count = 0;
+        for (int64_t i = ra; i <= hi; i++) {
+            if (p.seen[i]) continue;
+            const int64_t copies = 1 + (rb - i) / m;
+            const int64_t length = copies * m;
+            if (length < 10) {
+                // entropy of the motif, symbols accumulated in first-seen order
+                int cnt[4] = {0, 0, 0, 0};
+                int order[4], nd = 0;
+                for (int q = 0; q < m; q++) {
+                    uint8_t c = __ldg(t + i + q);
+                    int k = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
+                    if (cnt[k] == 0) order[nd++] = k;
+                    cnt[k]++;
+                }
+                double e = 0.0;
+                for (int q = 0; q < nd; q++) e -= p.plogp[m * 10 + cnt[order[q]]];
+                if (e < p.min_entropy) continue;
+            }
+            if (length < p.min_len) continue;
+            sink(i, i + length);
+            count++;
+        }
+        return count;
+    }
+};
+struct NullSink {
+    __device__ void operator()(int64_t, int64_t) const {}
+};
+struct CandSink {
+    int32_t *cpos, *cend;
+    unsigned long long *ckey;
+    uint32_t *cidx;
+    int64_t step;
+    int abits;
+    uint64_t at;
+    __device__ void operator()(int64_t i, int64_t e)
+    {
+        cpos[at] = (int32_t)i;
+        cend[at] = (int32_t)e;
+        ckey[at] = ((unsigned long long)(i % step) << abits) | (unsigned long long)i;
+        cidx[at] = (uint32_t)at;
+        at++;
+    }
+};
+struct CountRuns {
+    RunCand rc;
+    __device__ uint64_t operator()(int64_t r) const
+    {
+        NullSink s;
+        return (uint64_t)rc.visit(r, s);
+    }
+};
+struct EmitRuns {
+    RunCand rc;
+    int32_t *cpos, *cend;
+    unsigned long long *ckey;
+    uint32_t *cidx;
+    int64_t step;
+    __device__ void operator()(int64_t r, uint64_t excl, uint64_t cnt) const
+    {
+        if (!cnt) return;
+        CandSink s{cpos, cend, ckey, cidx, step, rc.abits, excl};
+        rc.visit(r, s);
+    }
+};
+
+// first run of every motif length in the sorted run list: off[u] = lower bound of
+// key >= (umax - u) << abits, u = 0..umax+1 (off[0] = number of runs)
+__global__ void run_offsets_kernel(const unsigned long long *__restrict__ key, int64_t m, int abits, int umax,
+                                   long long *__restrict__ off)
+{
+    int u = threadIdx.x;
+    if (u > umax + 1) return;
+    if (u == 0) { off[0] = m; return; }
+    if (u == umax + 1) { off[u] = 0; return; }
+    const unsigned long long want = (unsigned long long)(umax - u) << abits;
+    int64_t lo = 0, hi = m;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (key[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    off[u] = lo;
+}
 
 // ---- generic greedy replay ---------------------------------------------------
 // Cand: __device__ int64_t operator()(int64_t i)  -> array end if the reference's
@@ -513,22 +676,14 @@ static PassWs carve_pass_ws(Carver &c, int64_t n)
 // One greedy pass: positions [0, npos) are scanned with stride `step`, an emission
 // at c jumps to end(c); the scan stops at `limit`.  Appends rows at rec_base and
 // returns the number of emissions in *emitted.
-template <typename Cand, typename Writer>
-static int greedy_pass(int64_t npos, int64_t limit, int64_t step, int abits, Cand cand, Writer writer,
-                       const PassWs &w, int32_t *d_rec, int64_t rec_base, int64_t cap, int64_t *emitted,
-                       cudaStream_t st)
+// Replays the reference's walk over K candidates held in w (cpos/cend ascending, ckey0/cidx0).
+template <typename Writer>
+static int greedy_replay(int64_t K, int64_t limit, int64_t step, int abits, Writer writer, const PassWs &w,
+                         int32_t *d_rec, int64_t rec_base, int64_t cap, int64_t *emitted, cudaStream_t st)
 {
     *emitted = 0;
-    if (npos <= 0) return BWTK_OK;
-    CountCand<Cand> cc{cand};
-    EmitCand<Cand> ec{cand, w.cpos, w.cend, step, abits, w.ckey0, w.cidx0};
-    int rc = scan::run(npos, cc, ec, w.sws, st);
-    if (rc) return rc;
-    unsigned long long hK = 0;
-    BWTK_CUDA(cudaMemcpyAsync(&hK, w.sws.total, 8, cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaStreamSynchronize(st));
-    int64_t K = (int64_t)hK;
     if (K == 0) return BWTK_OK;
+    int rc;
     const unsigned long long *skey = w.ckey0;
     const uint32_t *sidx = w.cidx0;
     if (step > 1) {
@@ -567,10 +722,48 @@ static int greedy_pass(int64_t npos, int64_t limit, int64_t step, int abits, Can
     rc = scan::run(K, cp, ep, w.sws, st);
     if (rc) return rc;
     unsigned long long hE = 0;
-    BWTK_CUDA(cudaMemcpyAsync(&hE, w.sws.total, 8, cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaStreamSynchronize(st));
+    rc = read_back(&hE, w.sws.total, 8, st);
+    if (rc) return rc;
     *emitted = (int64_t)hE;
     return BWTK_OK;
+}
+
+// One greedy pass: positions [0, npos) are scanned with stride `step`, an emission
+// at c jumps to end(c); the scan stops at `limit`.  Appends rows at rec_base and
+// returns the number of emissions in *emitted.  Candidates: cand(i) for every position.
+template <typename Cand, typename Writer>
+static int greedy_pass(int64_t npos, int64_t limit, int64_t step, int abits, Cand cand, Writer writer,
+                       const PassWs &w, int32_t *d_rec, int64_t rec_base, int64_t cap, int64_t *emitted,
+                       cudaStream_t st)
+{
+    *emitted = 0;
+    if (npos <= 0) return BWTK_OK;
+    CountCand<Cand> cc{cand};
+    EmitCand<Cand> ec{cand, w.cpos, w.cend, step, abits, w.ckey0, w.cidx0};
+    int rc = scan::run(npos, cc, ec, w.sws, st);
+    if (rc) return rc;
+    unsigned long long hK = 0;
+    rc = read_back(&hK, w.sws.total, 8, st);
+    if (rc) return rc;
+    return greedy_replay((int64_t)hK, limit, step, abits, writer, w, d_rec, rec_base, cap, emitted, st);
+}
+
+// The same pass with the candidates expanded from `nruns` maximal runs (Tier 1).
+template <typename Writer>
+static int greedy_pass_runs(const RunCand &rcand, int64_t nruns, int64_t limit, int64_t step, Writer writer,
+                            const PassWs &w, int32_t *d_rec, int64_t rec_base, int64_t cap, int64_t *emitted,
+                            cudaStream_t st)
+{
+    *emitted = 0;
+    if (nruns <= 0) return BWTK_OK;
+    CountRuns cr{rcand};
+    EmitRuns er{rcand, w.cpos, w.cend, w.ckey0, w.cidx0, step};
+    int rc = scan::run(nruns, cr, er, w.sws, st);
+    if (rc) return rc;
+    unsigned long long hK = 0;
+    rc = read_back(&hK, w.sws.total, 8, st);
+    if (rc) return rc;
+    return greedy_replay((int64_t)hK, limit, step, rcand.abits, writer, w, d_rec, rec_base, cap, emitted, st);
 }
 
 // ---- strict adjacency with max_mismatch > 0 (bwt.py:1921-1999) -------------------
@@ -790,63 +983,22 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
     scan::Workspace sws = scan::carve(c, ccap);
     unsigned long long *d_count = c.take<unsigned long long>(2);
     if (!c.ok()) { set_error("strict workspace carve overflow"); return BWTK_EWORKSPACE; }
-    BWTK_CUDA(bwtk::zero_async(d_count, 16, st));
     BWTK_CUDA(bwtk::zero_async(rws.err, sizeof(int), st));
     BWTK_CUDA(bwtk::zero_async(sws.err, sizeof(int), st));
-
-    strict::CandOut out;
-    out.key = key0; out.val = val0; out.count = d_count; out.cap = ccap;
-    out.abits = strict::bits_for(n); out.umax = umax;
-
-    // units with (mc-1)*u < 8 take the per-position kernel, the rest the ballot kernel
-    int64_t small_hi = 7 / (min_copies - 1);
-    if (small_hi > umax) small_hi = umax;
-    if (small_hi >= min_unit_len) {
-        strict::find_runs_small_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_text, n, min_unit_len,
-                                                                                  small_hi, min_copies, out);
-        BWTK_LAUNCH_CHECK();
+    const unsigned long long *sk = nullptr;
+    const uint32_t *sv = nullptr;
+    int64_t m = 0;
+    int rc = strict::collect_runs(d_text, n, min_unit_len, umax, min_copies, key0, key1, val0, val1, d_count, ccap, rws,
+                                  st, &sk, &sv, &m);
+    if (rc == BWTK_EWORKSPACE) {
+        set_error("strict scan: %lld candidate runs exceed the workspace capacity %lld", (long long)m, (long long)ccap);
+        return rc;
     }
-    int64_t big_lo = small_hi + 1 > min_unit_len ? small_hi + 1 : min_unit_len;
-    if (big_lo <= umax) {
-        int64_t tiles = ceil_div(n, strict::TP);
-        int64_t nu = umax - big_lo + 1;
-        // enough CTAs to fill the machine even for short contigs
-        int64_t ysplit = ceil_div((int64_t)NUM_SMS * 8, tiles);
-        if (ysplit > nu) ysplit = nu;
-        if (ysplit < 1) ysplit = 1;
-        if (ysplit > 65535) ysplit = 65535;
-        int64_t u_per_block = ceil_div(nu, ysplit);
-        ysplit = ceil_div(nu, u_per_block);
-        size_t smem = (size_t)(strict::TP + umax + 16);
-        static size_t smem_set = 0;
-        if (smem > 48 * 1024 && smem > smem_set) {
-            BWTK_CUDA(cudaFuncSetAttribute(strict::find_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-            smem_set = smem;
-        }
-        dim3 grid((unsigned)tiles, (unsigned)ysplit);
-        strict::find_runs_kernel<<<grid, strict::THREADS, smem, st>>>(d_text, n, big_lo, umax, u_per_block,
-                                                                      min_copies, out);
-        BWTK_LAUNCH_CHECK();
-    }
-    unsigned long long h_cand = 0;
-    BWTK_CUDA(cudaMemcpyAsync(&h_cand, d_count, 8, cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaStreamSynchronize(st));
-    if ((int64_t)h_cand > ccap) {
-        set_error("strict scan: %llu candidate runs exceed the workspace capacity %lld", h_cand, (long long)ccap);
-        return BWTK_EWORKSPACE;
-    }
-    int64_t m = (int64_t)h_cand;
-    if (m == 0) return BWTK_OK;
-    int in_first = 1;
-    int rc = rsort::sort_pairs<unsigned long long>(key0, val0, key1, val1, m, 0,
-                                                   out.abits + strict::bits_for(umax), rws, st, &in_first,
-                                                   nullptr);
     if (rc) return rc;
-    const unsigned long long *sk = in_first ? key0 : key1;
-    const uint32_t *sv = in_first ? val0 : val1;
+    if (m == 0) return BWTK_OK;
+    const int abits_runs = strict::bits_for(n);
     strict::Resolved res{emit, rows};
-    strict::resolve_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(d_text, sk, sv, m, out.abits, umax,
+    strict::resolve_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(d_text, sk, sv, m, abits_runs, umax,
                                                                       min_copies, res);
     BWTK_LAUNCH_CHECK();
     strict::CountEmit ce{emit};
@@ -874,7 +1026,9 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
 extern "C" int64_t bwtk_tier1_workspace_bytes(int64_t n)
 {
     if (n < 1) n = 1;
-    return align_up(n, 256) + tier1::pass_ws_bytes(n) + 8192;  // seen mask + pass scratch + entropy table
+    const int64_t ccap = strict::cand_capacity(n);             // maximal runs of the motif lengths 1..9
+    return align_up(n, 256) + tier1::pass_ws_bytes(n) + 8192 +  // seen mask + pass scratch + entropy table
+           2 * align_up(ccap * 8, 256) + 2 * align_up(ccap * 4, 256) + 1024;
 }
 
 extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max_motif_len,
@@ -897,6 +1051,13 @@ extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max
     uint8_t *seen = c.take<uint8_t>(n);
     tier1::PassWs pw = tier1::carve_pass_ws(c, n);
     double *d_plogp = c.take<double>(100);
+    const int64_t ccap = strict::cand_capacity(n);
+    unsigned long long *rkey0 = c.take<unsigned long long>(ccap);
+    unsigned long long *rkey1 = c.take<unsigned long long>(ccap);
+    uint32_t *rval0 = c.take<uint32_t>(ccap);
+    uint32_t *rval1 = c.take<uint32_t>(ccap);
+    unsigned long long *d_runcount = c.take<unsigned long long>(2);
+    long long *d_runoff = c.take<long long>(16);
     if (!c.ok()) { set_error("tier1 workspace carve overflow"); return BWTK_EWORKSPACE; }
     BWTK_CUDA(bwtk::zero_async(seen, (size_t)n, st));
     BWTK_CUDA(bwtk::zero_async(pw.rws.err, sizeof(int), st));
@@ -917,13 +1078,42 @@ extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max
     const int abits = strict::bits_for(n);
     int64_t total = 0;
     int mmax = max_motif_len < 9 ? max_motif_len : 9;
+    // maximal runs of text[j]==text[j+m] for every motif length at once (min_copies >= 2: a
+    // candidate then sits inside a run; with min_copies == 1 every position is one)
+    const unsigned long long *rk = nullptr;
+    const uint32_t *rv = nullptr;
+    long long runoff[16] = {0};
+    bool by_runs = false;
+    if (min_copies >= 2 && mmax >= 1) {
+        int64_t nruns = 0;
+        int rc = strict::collect_runs(d_text, n, 1, mmax, min_copies, rkey0, rkey1, rval0, rval1, d_runcount, ccap,
+                                      pw.rws, st, &rk, &rv, &nruns);
+        if (rc && rc != BWTK_EWORKSPACE) return rc;
+        if (rc == BWTK_OK) {
+            by_runs = true;
+            if (nruns > 0) {
+                tier1::run_offsets_kernel<<<1, 32, 0, st>>>(rk, nruns, abits, mmax, d_runoff);
+                BWTK_LAUNCH_CHECK();
+                rc = read_back(runoff, d_runoff, sizeof(long long) * (size_t)(mmax + 2), st);
+                if (rc) return rc;
+            }
+        }   // more runs than the buffer holds (pathological text): per-position candidates below
+    }
     for (int m = mmax; m >= 1; m--) {
         if (n - m <= 0) continue;
         tier1::Params p{d_text, seen, n, m, min_copies, min_array_len, min_entropy, d_plogp};
-        tier1::Tier1Cand cand{p};
         tier1::Tier1Writer wr{m, seen};
         int64_t emitted = 0;
-        int rc = tier1::greedy_pass(n - m, n - m, step, abits, cand, wr, pw, d_rec, total, cap, &emitted, st);
+        int rc;
+        if (by_runs) {
+            // runs of length m occupy [off[m], off[m-1]) of the list sorted by (m descending, start)
+            const int64_t lo = runoff[m], hi = runoff[m - 1];
+            tier1::RunCand rcand{p, rk + lo, rv + lo, abits};
+            rc = tier1::greedy_pass_runs(rcand, hi - lo, n - m, step, wr, pw, d_rec, total, cap, &emitted, st);
+        } else {
+            tier1::Tier1Cand cand{p};
+            rc = tier1::greedy_pass(n - m, n - m, step, abits, cand, wr, pw, d_rec, total, cap, &emitted, st);
+        }
         if (rc) return rc;
         total += emitted;
     }
