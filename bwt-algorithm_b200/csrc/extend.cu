@@ -785,6 +785,27 @@ __global__ void place_rows_kernel(const int32_t *__restrict__ tmp, const int32_t
 
 using namespace bwtk;
 
+// The scratch of these entry points comes from the device's default stream-ordered pool.  With
+// the default release threshold (0) the pool hands everything back to the driver at every
+// synchronisation, so each call paid a fresh allocation of tens of MB (measured: 15 ms calls
+// with 100-500 ms outliers).  Keep freed blocks cached instead.
+static cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t st)
+{
+    static thread_local int tuned_device = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (tuned_device != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        tuned_device = dev;
+    }
+    return cudaMallocAsync(p, bytes, st);
+}
+
 static int max_of_periods(const int32_t *d_period, int64_t m, cudaStream_t st, int *out)
 {
     // small batches: read the periods back to size the scratch
@@ -815,7 +836,7 @@ extern "C" int32_t bwtk_extend_batch(const uint8_t *d_text, int64_t n, const int
     uint8_t *scratch = nullptr;
     int *d_err = nullptr;
     int64_t bytes = m * ext::scratch_per_thread(maxp) + 16;
-    BWTK_CUDA(cudaMallocAsync((void **)&scratch, (size_t)bytes, st));
+    BWTK_CUDA(pool_alloc((void **)&scratch, (size_t)bytes, st));
     d_err = (int *)(scratch + bytes - 16);
     BWTK_CUDA(bwtk::zero_async(d_err, 4, st));
     ext::extend_batch_kernel<<<(unsigned)ceil_div(m, 64), 64, 0, st>>>(d_text, n, d_seed, d_period, d_flags, m,
@@ -843,7 +864,7 @@ extern "C" int32_t bwtk_consensus_batch(const uint8_t *d_text, int64_t text_size
     BWTK_REQUIRE(maxp <= 65535, "period too long");
     uint8_t *scratch = nullptr;
     int64_t bytes = m * ext::scratch_per_thread(maxp) + 16;
-    BWTK_CUDA(cudaMallocAsync((void **)&scratch, (size_t)bytes, st));
+    BWTK_CUDA(pool_alloc((void **)&scratch, (size_t)bytes, st));
     int *d_err = (int *)(scratch + bytes - 16);
     BWTK_CUDA(bwtk::zero_async(d_err, 4, st));
     ext::consensus_batch_kernel<<<(unsigned)ceil_div(m, 64), 64, 0, st>>>(
@@ -910,7 +931,7 @@ extern "C" int32_t bwtk_period_scan(const uint8_t *d_text, int64_t n_total, int6
     int64_t bytes = align_up(sc_bytes, 256) + align_up(tmp_cap * BWTK_REC_W * 4, 256) +
                     align_up(tmp_cap * 16, 256) + 4 * align_up((npass + 2) * 8, 256) + 1024;
     uint8_t *buf = nullptr;
-    BWTK_CUDA(cudaMallocAsync((void **)&buf, (size_t)bytes, st));
+    BWTK_CUDA(pool_alloc((void **)&buf, (size_t)bytes, st));
     Carver c(buf, bytes);
     uint8_t *scratch = c.take<uint8_t>(sc_bytes);
     int32_t *tmp = c.take<int32_t>(tmp_cap * BWTK_REC_W);
