@@ -9,9 +9,12 @@
 // copy; here a per-column symbol tally is kept and updated incrementally
 // (total mismatches = cells - sum of column maxima; consensus = first maximum =
 // smallest byte on ties), which is the same decision at O(copies*period).
-// The period scan runs one thread per period pass; the reference's global
-// 100 000-iteration budget is applied afterwards from the per-pass visit
-// counts, so the passes stay independent.
+// The period scan runs one CTA per period pass: 128 speculative visits per
+// iteration, the first survivor evaluated in full by a whole warp.  All passes run
+// at once with the full 100 000-visit budget; the reference's GLOBAL budget is
+// applied afterwards from the per-pass visit counts (rows past a pass's share are
+// dropped), and a pass stops early as soon as its predecessors have finished and it
+// knows what they left it.
 #include "common.cuh"
 
 namespace bwtk {
@@ -587,11 +590,17 @@ __global__ void __launch_bounds__(PASS_THREADS)
     period_pass_kernel(ScanCfg c, int64_t npass, const int64_t *__restrict__ budget,
                        int64_t *__restrict__ visits, int64_t *__restrict__ emits,
                        int32_t *__restrict__ tmp, int32_t *__restrict__ tmp_aux, int64_t tmp_cap,
-                       unsigned long long *tmp_count, uint8_t *scratch, int maxp, int *err)
+                       unsigned long long *tmp_count, uint8_t *scratch, int maxp, int *err,
+                       volatile long long *done)
 {
     const int64_t pass = blockIdx.x;
     if (pass >= npass) return;
     __shared__ int64_t s_i, s_it, s_seq;
+    // speculative run (budget == nullptr): done[q] = visits of pass q + 1 once it has finished.
+    // A pass adds up its predecessors as they finish and, once all have, knows what the global
+    // budget leaves it and stops there instead of walking the whole contig.
+    __shared__ int64_t s_allowed, s_prev_sum;
+    __shared__ int s_known, s_learned;
     __shared__ int s_first[PASS_THREADS / 32];
     __shared__ int s_stop;
     constexpr int MEMO = 4;
@@ -608,13 +617,30 @@ __global__ void __launch_bounds__(PASS_THREADS)
     Tally t = make_tally(my, maxp);
     uint8_t *cons = t.nsym + maxp;
     const int64_t n = c.n;
-    const int64_t allowed = budget ? budget[pass] : MAX_ITER;
     if (tid == 0) {
+        s_allowed = budget ? budget[pass] : MAX_ITER;
+        s_prev_sum = 0; s_known = 0; s_learned = 0;
         s_i = 0; s_it = 0; s_seq = 0; s_memo_next = 0; s_last_full = -1; s_ff = 0;
         for (int q = 0; q < MEMO; q++) { s_memo_x[q] = -1; s_memo_it[q] = -1; }
     }
     __syncthreads();
     while (p > 0) {
+        if (done && tid == 0 && !s_learned) {
+            while (s_known < (int)pass) {
+                const long long d = done[s_known];
+                if (d == 0) break;
+                s_prev_sum += d - 1;
+                s_known++;
+            }
+            if (s_known == (int)pass) {
+                int64_t left = MAX_ITER - s_prev_sum;
+                if (left < 0) left = 0;
+                if (left < s_allowed) s_allowed = left;
+                s_learned = 1;
+            }
+        }
+        __syncthreads();
+        const int64_t allowed = s_allowed;
         const int64_t i0 = s_i, it0 = s_it;
         if (i0 + 2 * (int64_t)p > n || it0 >= allowed) break;
         // visit number it0 + tid at position i0 + tid*step
@@ -735,8 +761,16 @@ __global__ void __launch_bounds__(PASS_THREADS)
         }
     }
     if (tid == 0) {
-        if (visits) visits[pass] = s_it;
+        // a pass cut short by the learned budget would have gone on: report more than it was left,
+        // which is all budget_kernel needs to know (it clamps, and notes that the cap was hit)
+        int64_t v = s_it;
+        if (done && s_learned && p > 0 && s_it >= s_allowed && s_i + 2 * (int64_t)p <= n) v = s_allowed + 1;
+        if (visits) visits[pass] = v;
         if (emits) emits[pass] = s_seq;
+        if (done) {
+            __threadfence();
+            done[pass] = v + 1;
+        }
     }
 }
 
@@ -770,11 +804,23 @@ __global__ void offsets_kernel(const int64_t *__restrict__ emits, int64_t npass,
     offs[npass] = acc;
 }
 
-__global__ void place_rows_kernel(const int32_t *__restrict__ tmp, const int32_t *__restrict__ aux, int64_t m,
-                                  const int64_t *__restrict__ offs, int32_t *__restrict__ out, int64_t cap)
+// rows of every pass that fall inside its budget (aux = pass, sequence number, visit count)
+__global__ void count_within_budget_kernel(const int32_t *__restrict__ aux, int64_t m,
+                                           const int64_t *__restrict__ budget, unsigned long long *emits)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
+    const int pass = aux[i * 4];
+    if ((int64_t)aux[i * 4 + 2] <= budget[pass]) atomicAdd(&emits[pass], 1ull);
+}
+
+__global__ void place_rows_kernel(const int32_t *__restrict__ tmp, const int32_t *__restrict__ aux, int64_t m,
+                                  const int64_t *__restrict__ offs, const int64_t *__restrict__ budget,
+                                  int32_t *__restrict__ out, int64_t cap)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (budget && (int64_t)aux[i * 4 + 2] > budget[aux[i * 4]]) return;   // emitted past the pass's budget
     int64_t at = offs[aux[i * 4]] + aux[i * 4 + 1];
     if (at >= cap) return;
     for (int q = 0; q < BWTK_REC_W; q++) out[at * BWTK_REC_W + q] = tmp[i * BWTK_REC_W + q];
@@ -929,7 +975,7 @@ extern "C" int32_t bwtk_period_scan(const uint8_t *d_text, int64_t n_total, int6
     int64_t tmp_cap = cap > 65536 ? cap : 65536;
     int64_t sc_bytes = npass * ext::scratch_per_thread(maxp);
     int64_t bytes = align_up(sc_bytes, 256) + align_up(tmp_cap * BWTK_REC_W * 4, 256) +
-                    align_up(tmp_cap * 16, 256) + 4 * align_up((npass + 2) * 8, 256) + 1024;
+                    align_up(tmp_cap * 16, 256) + 5 * align_up((npass + 2) * 8, 256) + 1024;
     uint8_t *buf = nullptr;
     BWTK_CUDA(pool_alloc((void **)&buf, (size_t)bytes, st));
     Carver c(buf, bytes);
@@ -941,31 +987,52 @@ extern "C" int32_t bwtk_period_scan(const uint8_t *d_text, int64_t n_total, int6
     int64_t *budget = c.take<int64_t>(npass + 2);
     int64_t *offs = c.take<int64_t>(npass + 2);
     unsigned long long *tmp_count = c.take<unsigned long long>(2);
+    long long *d_done = c.take<long long>(npass + 2);
     int64_t *d_iter = c.take<int64_t>(2);
     int *d_err = c.take<int>(4);
     BWTK_CUDA(bwtk::zero_async(tmp_count, 16, st));
     BWTK_CUDA(bwtk::zero_async(d_err, 4, st));
     unsigned grid = (unsigned)npass;
-    // run 1: visits per pass with an unlimited (MAX_ITER) budget each
-    ext::period_pass_kernel<<<grid, ext::PASS_THREADS, 0, st>>>(cfg, npass, nullptr, visits, nullptr, nullptr, nullptr, 0,
-                                                 tmp_count, scratch, maxp, d_err);
+    // One speculative run: every pass walks with the full budget and appends its rows with the
+    // visit count at which each was emitted.  The reference's global 100 000-visit budget is then
+    // applied afterwards: pass q may spend what the earlier passes left, and its rows past that
+    // point are dropped (they form a suffix of the pass).  Only if the speculative rows overflow
+    // the buffer (cycles fast-forwarded under a budget they will not get) is the walk repeated
+    // with the real budgets.
+    BWTK_CUDA(bwtk::zero_async(d_done, (size_t)(npass + 2) * 8, st));
+    ext::period_pass_kernel<<<grid, ext::PASS_THREADS, 0, st>>>(cfg, npass, nullptr, visits, emits, tmp, aux, tmp_cap,
+                                                 tmp_count, scratch, maxp, d_err, d_done);
     BWTK_LAUNCH_CHECK();
     ext::budget_kernel<<<1, 32, 0, st>>>(visits, npass, budget, d_iter);
     BWTK_LAUNCH_CHECK();
-    // run 2: same walk, bounded by the global budget, rows appended
-    ext::period_pass_kernel<<<grid, ext::PASS_THREADS, 0, st>>>(cfg, npass, budget, nullptr, emits, tmp, aux, tmp_cap, tmp_count,
-                                                 scratch, maxp, d_err);
-    BWTK_LAUNCH_CHECK();
+    unsigned long long h_m = 0;
+    int rc = read_back(&h_m, tmp_count, 8, st);
+    if (rc) { cudaFreeAsync(buf, st); return rc; }
+    const int64_t *row_budget = budget;
+    if ((int64_t)h_m > tmp_cap) {
+        BWTK_CUDA(bwtk::zero_async(tmp_count, 16, st));
+        ext::period_pass_kernel<<<grid, ext::PASS_THREADS, 0, st>>>(cfg, npass, budget, nullptr, emits, tmp, aux, tmp_cap,
+                                                     tmp_count, scratch, maxp, d_err, nullptr);
+        BWTK_LAUNCH_CHECK();
+        rc = read_back(&h_m, tmp_count, 8, st);
+        if (rc) { cudaFreeAsync(buf, st); return rc; }
+        row_budget = nullptr;   // every row of this run is inside its budget
+    } else if (h_m > 0) {
+        BWTK_CUDA(bwtk::zero_async(emits, (size_t)(npass + 2) * 8, st));
+        ext::count_within_budget_kernel<<<(unsigned)ceil_div((int64_t)h_m, 256), 256, 0, st>>>(
+            aux, (int64_t)h_m, budget, reinterpret_cast<unsigned long long *>(emits));
+        BWTK_LAUNCH_CHECK();
+    } else {
+        BWTK_CUDA(bwtk::zero_async(emits, (size_t)(npass + 2) * 8, st));
+    }
     ext::offsets_kernel<<<1, 32, 0, st>>>(emits, npass, offs);
     BWTK_LAUNCH_CHECK();
-    unsigned long long h_m = 0;
     int h_err = 0;
-    int64_t h_it = 0;
-    BWTK_CUDA(cudaMemcpyAsync(&h_m, tmp_count, 8, cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaMemcpyAsync(&h_it, d_iter, 8, cudaMemcpyDeviceToHost, st));
-    BWTK_CUDA(cudaStreamSynchronize(st));
-    int rc = BWTK_OK;
+    int64_t h_it = 0, h_total = 0;
+    rc = read_back(&h_err, d_err, 4, st);
+    if (!rc) rc = read_back(&h_it, d_iter, 8, st);
+    if (!rc) rc = read_back(&h_total, offs + npass, 8, st);
+    if (rc) { cudaFreeAsync(buf, st); return rc; }
     if (h_err) {
         set_error("period scan: more than %d distinct symbols in one column", ext::SLOTS);
         rc = BWTK_EINVAL;
@@ -974,14 +1041,14 @@ extern "C" int32_t bwtk_period_scan(const uint8_t *d_text, int64_t n_total, int6
         set_error("period scan: %llu records exceed capacity %lld", h_m, (long long)tmp_cap);
         rc = BWTK_EOVERFLOW;
     } else {
-        *h_count = (int64_t)h_m;
+        *h_count = h_total;
         *h_iterations = h_it;
-        if ((int64_t)h_m > cap) {
-            set_error("period scan: %llu records exceed capacity %lld", h_m, (long long)cap);
+        if (h_total > cap) {
+            set_error("period scan: %lld records exceed capacity %lld", (long long)h_total, (long long)cap);
             rc = BWTK_EOVERFLOW;
-        } else if (h_m > 0) {
+        } else if (h_total > 0) {
             ext::place_rows_kernel<<<(unsigned)ceil_div((int64_t)h_m, 256), 256, 0, st>>>(tmp, aux, (int64_t)h_m,
-                                                                                         offs, d_rec, cap);
+                                                                                         offs, row_budget, d_rec, cap);
             bwtk::count_launch();
             if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
                 set_error("place_rows failed");

@@ -43,6 +43,10 @@ def test_product_has_no_cpu_fallback():
         bwt.BWTCore("ACGTACGT$")
     with pytest.raises(_lib.BwtkError):
         bwt.Tier1STRFinder(np.frombuffer(b"ACACACACAC", np.uint8)).find_strs("c")
+    from bwt_algorithm_b200.streaming import IndexPipeline
+
+    with pytest.raises(_lib.BwtkError):
+        IndexPipeline(1000)
 
 
 def test_product_never_imports_the_oracle():
