@@ -401,83 +401,101 @@ struct RunCand {
     const unsigned long long *rkey;   // runs of this motif length, sorted by start (low abits)
     const uint32_t *rend;
     int abits;
-    // calls sink(i, array_end) for the candidates of run r in ascending order; returns their number
-    template <typename Sink> __device__ int64_t visit(int64_t r, Sink &sink) const
+    __device__ __forceinline__ void bounds(int64_t r, int64_t &ra, int64_t &rb, int64_t &hi) const
+    {
+        ra = (int64_t)(rkey[r] & ((1ull << abits) - 1ull));
+        rb = (int64_t)rend[r];
+        hi = rb - (int64_t)(p.mc - 1) * p.m;          // last position with enough run left
+        if (hi > p.n - p.m - 1) hi = p.n - p.m - 1;
+    }
+    // the run region has period m: a non-ACGT symbol among its first m is in every window
+    __device__ __forceinline__ bool motif_is_acgt(int64_t ra) const
+    {
+        for (int q = 0; q < p.m; q++)
+            if (!acgt(__ldg(p.text + ra + q))) return false;
+        return true;
+    }
+    // array end if position i of a run ending at rb is a candidate, else -1 (would_emit's tail)
+    __device__ __forceinline__ int64_t test(int64_t i, int64_t rb) const
     {
         const int m = p.m;
-        const uint8_t *t = p.text;
-        const int64_t ra = (int64_t)(rkey[r] & ((1ull << abits) - 1ull)), rb = (int64_t)rend[r];
-        // the run region has period m: a non-ACGT symbol among its first m is in every window
-        for (int q = 0; q < m; q++)
-            if (!acgt(__ldg(t + ra + q))) return 0;
-        const int64_t need = (int64_t)(p.mc - 1) * m;
-        int64_t hi = rb - need;
-        if (hi > p.n - m - 1) hi = p.n - m - 1;
-        int64_t count = 0;
-        for (int64_t i = ra; i <= hi; i++) {
-            if (p.seen[i]) continue;
-            const int64_t copies = 1 + (rb - i) / m;
-            const int64_t length = copies * m;
-            if (length < 10) {
-                // entropy of the motif, symbols accumulated in first-seen order
-                int cnt[4] = {0, 0, 0, 0};
-                int order[4], nd = 0;
-                for (int q = 0; q < m; q++) {
-                    uint8_t c = __ldg(t + i + q);
-                    int k = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
-                    if (cnt[k] == 0) order[nd++] = k;
-                    cnt[k]++;
-                }
-                double e = 0.0;
-                for (int q = 0; q < nd; q++) e -= p.plogp[m * 10 + cnt[order[q]]];
-                if (e < p.min_entropy) continue;
+        if (p.seen[i]) return -1;
+        const int64_t copies = 1 + (rb - i) / m;
+        const int64_t length = copies * m;
+        if (length < 10) {
+            // entropy of the motif, symbols accumulated in first-seen order
+            int cnt[4] = {0, 0, 0, 0};
+            int order[4], nd = 0;
+            for (int q = 0; q < m; q++) {
+                uint8_t c = __ldg(p.text + i + q);
+                int k = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
+                if (cnt[k] == 0) order[nd++] = k;
+                cnt[k]++;
             }
-            if (length < p.min_len) continue;
-            sink(i, i + length);
-            count++;
+            double e = 0.0;
+            for (int q = 0; q < nd; q++) e -= p.plogp[m * 10 + cnt[order[q]]];
+            if (e < p.min_entropy) return -1;
         }
-        return count;
+        if (length < p.min_len) return -1;
+        return i + length;
     }
 };
-struct NullSink {
-    __device__ void operator()(int64_t, int64_t) const {}
-};
-struct CandSink {
-    int32_t *cpos, *cend;
-    unsigned long long *ckey;
-    uint32_t *cidx;
-    int64_t step;
-    int abits;
-    uint64_t at;
-    __device__ void operator()(int64_t i, int64_t e)
-    {
-        cpos[at] = (int32_t)i;
-        cend[at] = (int32_t)e;
-        ckey[at] = ((unsigned long long)(i % step) << abits) | (unsigned long long)i;
-        cidx[at] = (uint32_t)at;
-        at++;
+
+// one warp per run: number of candidates of every run
+__global__ void __launch_bounds__(256)
+    run_count_kernel(RunCand rc, int64_t nruns, uint32_t *__restrict__ cnt)
+{
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= nruns) return;
+    const int lane = threadIdx.x & 31;
+    int64_t ra, rb, hi;
+    rc.bounds(r, ra, rb, hi);
+    uint32_t total = 0;
+    if (rc.motif_is_acgt(ra)) {
+        for (int64_t i0 = ra; i0 <= hi; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const bool ok = i <= hi && rc.test(i, rb) >= 0;
+            total += (uint32_t)__popc(__ballot_sync(0xffffffffu, ok));
+        }
     }
-};
-struct CountRuns {
-    RunCand rc;
-    __device__ uint64_t operator()(int64_t r) const
-    {
-        NullSink s;
-        return (uint64_t)rc.visit(r, s);
+    if (lane == 0) cnt[r] = total;
+}
+
+// one warp per run: the candidates in ascending position order at off[r]..
+__global__ void __launch_bounds__(256)
+    run_emit_kernel(RunCand rc, int64_t nruns, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ off,
+                    int32_t *__restrict__ cpos, int32_t *__restrict__ cend, unsigned long long *__restrict__ ckey,
+                    uint32_t *__restrict__ cidx, int64_t step)
+{
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= nruns) return;
+    if (cnt[r] == 0) return;
+    const int lane = threadIdx.x & 31;
+    int64_t ra, rb, hi;
+    rc.bounds(r, ra, rb, hi);
+    uint32_t at = off[r];
+    for (int64_t i0 = ra; i0 <= hi; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const int64_t e = i <= hi ? rc.test(i, rb) : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, e >= 0);
+        if (e >= 0) {
+            const uint32_t s = at + (uint32_t)__popc(bal & lanemask_lt());
+            cpos[s] = (int32_t)i;
+            cend[s] = (int32_t)e;
+            ckey[s] = ((unsigned long long)(i % step) << rc.abits) | (unsigned long long)i;
+            cidx[s] = s;
+        }
+        at += (uint32_t)__popc(bal);
     }
+}
+
+struct CountArr {
+    const uint32_t *cnt;
+    __device__ uint64_t operator()(int64_t r) const { return cnt[r]; }
 };
-struct EmitRuns {
-    RunCand rc;
-    int32_t *cpos, *cend;
-    unsigned long long *ckey;
-    uint32_t *cidx;
-    int64_t step;
-    __device__ void operator()(int64_t r, uint64_t excl, uint64_t cnt) const
-    {
-        if (!cnt) return;
-        CandSink s{cpos, cend, ckey, cidx, step, rc.abits, excl};
-        rc.visit(r, s);
-    }
+struct StoreOffset {
+    uint32_t *off;
+    __device__ void operator()(int64_t r, uint64_t excl, uint64_t) const { off[r] = (uint32_t)excl; }
 };
 
 // first run of every motif length in the sorted run list: off[u] = lower bound of
@@ -677,9 +695,11 @@ static PassWs carve_pass_ws(Carver &c, int64_t n)
 // at c jumps to end(c); the scan stops at `limit`.  Appends rows at rec_base and
 // returns the number of emissions in *emitted.
 // Replays the reference's walk over K candidates held in w (cpos/cend ascending, ckey0/cidx0).
+// `path_bound`: an upper bound of the number of candidates on the visited path (K if unknown).
 template <typename Writer>
-static int greedy_replay(int64_t K, int64_t limit, int64_t step, int abits, Writer writer, const PassWs &w,
-                         int32_t *d_rec, int64_t rec_base, int64_t cap, int64_t *emitted, cudaStream_t st)
+static int greedy_replay(int64_t K, int64_t path_bound, int64_t limit, int64_t step, int abits, Writer writer,
+                         const PassWs &w, int32_t *d_rec, int64_t rec_base, int64_t cap, int64_t *emitted,
+                         cudaStream_t st)
 {
     *emitted = 0;
     if (K == 0) return BWTK_OK;
@@ -699,9 +719,11 @@ static int greedy_replay(int64_t K, int64_t limit, int64_t step, int abits, Writ
     succ_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(w.cend, skey, sidx, K, step, abits, limit, w.succ,
                                                           w.d_first);
     BWTK_LAUNCH_CHECK();
-    // jump table for 2^kappa hops, kappa ~ log2(K)/2
+    // jump table for 2^kappa hops, kappa ~ log2(path length)/2: the coarse walk (one thread) then
+    // takes ~sqrt(path) jumps and every fine walk ~sqrt(path) hops
+    const int64_t plen = path_bound > 0 && path_bound < K ? path_bound : K;
     int kappa = 0;
-    while ((1ll << (2 * kappa)) < K) kappa++;
+    while ((1ll << (2 * kappa)) < plen) kappa++;
     const int32_t *jbig = w.succ;
     int32_t *ja = w.j0, *jb = w.j1;
     for (int r = 0; r < kappa; r++) {
@@ -713,7 +735,7 @@ static int greedy_replay(int64_t K, int64_t limit, int64_t step, int abits, Writ
     coarse_walk_kernel<<<1, 32, 0, st>>>(jbig, w.d_first, w.anchor, w.d_nanchor);
     BWTK_LAUNCH_CHECK();
     BWTK_CUDA(bwtk::zero_async(w.onpath, (size_t)K, st));
-    int64_t max_anchor = (K >> kappa) + 2;
+    int64_t max_anchor = (plen >> kappa) + 2;
     fine_walk_kernel<<<(unsigned)ceil_div(max_anchor, 128), 128, 0, st>>>(w.succ, w.anchor, w.d_nanchor,
                                                                         1ll << kappa, w.onpath);
     BWTK_LAUNCH_CHECK();
@@ -745,10 +767,12 @@ static int greedy_pass(int64_t npos, int64_t limit, int64_t step, int abits, Can
     unsigned long long hK = 0;
     rc = read_back(&hK, w.sws.total, 8, st);
     if (rc) return rc;
-    return greedy_replay((int64_t)hK, limit, step, abits, writer, w, d_rec, rec_base, cap, emitted, st);
+    return greedy_replay((int64_t)hK, (int64_t)hK, limit, step, abits, writer, w, d_rec, rec_base, cap, emitted, st);
 }
 
-// The same pass with the candidates expanded from `nruns` maximal runs (Tier 1).
+// The same pass with the candidates expanded from `nruns` maximal runs (Tier 1): a warp per run
+// counts, the counts are scanned, a warp per run writes.  An emission jumps past its run, so the
+// visited path has at most `nruns` candidates, which sizes the two-level walk.
 template <typename Writer>
 static int greedy_pass_runs(const RunCand &rcand, int64_t nruns, int64_t limit, int64_t step, Writer writer,
                             const PassWs &w, int32_t *d_rec, int64_t rec_base, int64_t cap, int64_t *emitted,
@@ -756,14 +780,20 @@ static int greedy_pass_runs(const RunCand &rcand, int64_t nruns, int64_t limit, 
 {
     *emitted = 0;
     if (nruns <= 0) return BWTK_OK;
-    CountRuns cr{rcand};
-    EmitRuns er{rcand, w.cpos, w.cend, w.ckey0, w.cidx0, step};
-    int rc = scan::run(nruns, cr, er, w.sws, st);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(w.j0), *off = reinterpret_cast<uint32_t *>(w.j1);   // free until the replay
+    run_count_kernel<<<(unsigned)ceil_div(nruns, 8), 256, 0, st>>>(rcand, nruns, cnt);
+    BWTK_LAUNCH_CHECK();
+    CountArr ca{cnt};
+    StoreOffset so{off};
+    int rc = scan::run(nruns, ca, so, w.sws, st);
     if (rc) return rc;
+    run_emit_kernel<<<(unsigned)ceil_div(nruns, 8), 256, 0, st>>>(rcand, nruns, cnt, off, w.cpos, w.cend, w.ckey0,
+                                                                 w.cidx0, step);
+    BWTK_LAUNCH_CHECK();
     unsigned long long hK = 0;
     rc = read_back(&hK, w.sws.total, 8, st);
     if (rc) return rc;
-    return greedy_replay((int64_t)hK, limit, step, rcand.abits, writer, w, d_rec, rec_base, cap, emitted, st);
+    return greedy_replay((int64_t)hK, nruns, limit, step, rcand.abits, writer, w, d_rec, rec_base, cap, emitted, st);
 }
 
 // ---- strict adjacency with max_mismatch > 0 (bwt.py:1921-1999) -------------------
