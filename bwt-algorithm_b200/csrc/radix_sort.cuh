@@ -1,12 +1,14 @@
 // radix_sort.cuh -- LSD radix sort of (key, uint32 value) pairs, one global
 // read + one global write per pass ("onesweep": per-tile digit offsets come from
 // a decoupled look-back over tile status words, global digit bases from one
-// up-front histogram of every pass).  Ranking inside a tile uses warp-level
-// match masks (issued four at a time for ILP) and one shared-memory atomic per
-// distinct digit per warp step; scatters are staged through shared memory so
-// global stores are contiguous per digit.  Stable.  Keys are uint32_t or
-// uint64_t.  The first pass can read its pairs from a generator (Source) instead
-// of arrays, e.g. suffix keys straight from the bit-packed text.
+// up-front histogram of every pass).  Ranking inside a tile: the peer mask of
+// equal digits comes from one ballot per digit bit (PTX, see refine_peers;
+// match.any is bound by the address-divergence unit), four keys in flight for
+// ILP, and one shared-memory atomic per distinct digit per warp step; scatters
+// are staged through shared memory so global stores are contiguous per digit.
+// Stable.  Keys are uint32_t or uint64_t.  The first pass can read its pairs
+// from a generator (Source) instead of arrays, e.g. suffix keys straight from
+// the bit-packed text, whose digit histograms are all one chunk histogram.
 #pragma once
 #include <type_traits>
 

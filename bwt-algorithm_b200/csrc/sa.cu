@@ -66,7 +66,7 @@ struct RgComb {
 
 // Round-0 singletons never get their rank scattered (that scatter is 46.7 M random
 // 4-byte writes for a chr21-sized contig, ~3 GB of DRAM traffic, while the doubling
-// rounds only ever read the ranks of ~10 % of the suffixes).  Their rank is their
+// rounds only ever read the ranks of ~6 % of the suffixes).  Their rank is their
 // SA position, recovered on demand: 16-bit prefix table -> binary search in the
 // sorted round-0 keys -> step over the (<= 15) short suffixes of that key.
 struct LazyRank {
