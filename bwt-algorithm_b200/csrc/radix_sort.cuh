@@ -20,7 +20,7 @@ namespace rsort {
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 #ifndef BWTK_RS_THREADS
-#define BWTK_RS_THREADS 256
+#define BWTK_RS_THREADS 512
 #endif
 #ifndef BWTK_RS_ITEMS
 #define BWTK_RS_ITEMS 16
@@ -29,10 +29,10 @@ constexpr int RADIX = 1 << RADIX_BITS;
 #define BWTK_RS_WINDOW 4
 #endif
 #ifndef BWTK_RS_MINB32
-#define BWTK_RS_MINB32 3
+#define BWTK_RS_MINB32 2
 #endif
 #ifndef BWTK_RS_MINB64
-#define BWTK_RS_MINB64 2
+#define BWTK_RS_MINB64 1
 #endif
 constexpr int THREADS = BWTK_RS_THREADS;
 constexpr int WARPS = THREADS / 32;
