@@ -86,10 +86,17 @@ class IndexPipeline:
                            "upload_text")
             else:
                 slot.d_text[:n].copy_(t, non_blocking=True)
-            rc = L.bwtk_index_build(slot.d_text.data_ptr(), n, self.occ_rate, slot.sa.data_ptr(), None,
-                                    slot.bwt.data_ptr(), slot.occ.data_ptr(), slot.rows_cap, _lib.ptr(slot.lcp),
-                                    slot.totals.ctypes.data, slot.row.ctypes.data, slot.stats.ctypes.data,
-                                    slot.ws.data_ptr(), slot.ws.numel(), slot.stream.cuda_stream)
+            for _attempt in range(2):
+                rc = L.bwtk_index_build(slot.d_text.data_ptr(), n, self.occ_rate, slot.sa.data_ptr(), None,
+                                        slot.bwt.data_ptr(), slot.occ.data_ptr(), slot.rows_cap, _lib.ptr(slot.lcp),
+                                        slot.totals.ctypes.data, slot.row.ctypes.data, slot.stats.ctypes.data,
+                                        slot.ws.data_ptr(), slot.ws.numel(), slot.stream.cuda_stream)
+                if rc == _lib.E_OVERFLOW and slot.stats[7] > slot.rows_cap:
+                    # more than 8 distinct byte values (IUPAC codes, soft-masked text): a taller Occ matrix
+                    slot.rows_cap = int(slot.stats[7])
+                    slot.occ = torch.zeros((slot.rows_cap, slot.ncp_cap), dtype=torch.int32, device=self.device)
+                    continue
+                break
             _lib.check(rc, "index_build")
             slot.built.record()
         # All downloads go through ONE stream, in order.  A download enqueued on its own stream

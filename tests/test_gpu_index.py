@@ -212,6 +212,7 @@ def test_index_pipeline_overlapped_builds(DeviceIndex, oracle):
     from bwt_algorithm_b200.streaming import IndexPipeline
 
     texts = [gen_contig(n, 60 + i).tobytes() + b"$" for i, n in enumerate((90_000, 30_000, 120_000, 5, 64_000))]
+    texts.insert(2, b"ACGTRYKMSWNacgtn" * 700 + b"$")      # > 8 distinct bytes: the slot grows its Occ matrix
     pipe = IndexPipeline(max(len(t) for t in texts), slots=2)
     tickets = []
     results = {}
