@@ -363,7 +363,10 @@ def run_ours(args):
 
     if rank == 0:
         value = world * args.n * args.steps / (total_ms * 1e-3) / 1e9
-        e2e_val = world * args.n * args.steps / (e2e_ms * 1e-3) / 1e9
+        # one or two contigs in flight per GPU, whichever moved more bases: with many GPUs on one host the
+        # host's memory system (not PCIe) limits the downloads and the second stream only adds contention
+        e2e_best_ms = min(e2e_ms, e2e_serial_ms)
+        e2e_val = world * args.n * args.steps / (e2e_best_ms * 1e-3) / 1e9
         peak, peak_src = measured_peak()
         out = {
             "metric": "SA+BWT+LCP Gbases/s", "value": round(value, 4), "unit": "Gbases/s", "n_gpus": world,
@@ -374,8 +377,11 @@ def run_ours(args):
                        "generator": "SURVEY Appendix B gen_contig(seed=21+rank)", "occ_rate": 128,
                        "l2": "256 MB write between timed steps (flush)", "parallelism": f"contig-per-gpu x{world}"},
             "e2e": {"value": round(e2e_val, 4), "unit": "Gbases/s", "h2d_bytes_per_step": h2d_b,
-                    "d2h_bytes_per_step": d2h_b, "ms_per_step": round(e2e_ms / args.steps, 4),
-                    "in_flight": 2, "api": "bwt_algorithm_b200.streaming.IndexPipeline -> bwtk_index_build",
+                    "d2h_bytes_per_step": d2h_b, "ms_per_step": round(e2e_best_ms / args.steps, 4),
+                    "in_flight": 2 if e2e_ms <= e2e_serial_ms else 1,
+                    "api": "bwt_algorithm_b200.streaming.IndexPipeline -> bwtk_index_build",
+                    "pipelined_ms_per_step": round(e2e_ms / args.steps, 4),
+                    "pipelined_value": round(world * args.n * args.steps / (e2e_ms * 1e-3) / 1e9, 4),
                     "serial_ms_per_step": round(e2e_serial_ms / args.steps, 4),
                     "serial_value": round(world * args.n * args.steps / (e2e_serial_ms * 1e-3) / 1e9, 4),
                     "l2": "no flush between pipelined steps: each contig touches ~2 GB >> 126 MB L2"},
