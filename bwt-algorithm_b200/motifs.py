@@ -111,6 +111,8 @@ class MotifUtils:
         return row[-1]
 
     # ---- per-copy alignment (bwt.py:828-1102) ------------------------------
+    _EXACT_COPY_FAST_PATH = True   # tests switch it off to compare with the DP-only walk
+
     @staticmethod
     def _align_unit_to_window(motif: str, window: str, max_indel: int,
                               mismatch_tolerance: int) -> Optional[AlignmentResult]:
@@ -257,6 +259,19 @@ class MotifUtils:
             window = sequence[pos:min(total, pos + k + max_indel)]
             if len(window) < k - max_indel:
                 break
+            if MotifUtils._EXACT_COPY_FAST_PATH and window.startswith(template):
+                # Exact copy: the banded DP would return the all-diagonal alignment (cost 0 at
+                # column k, every shorter end column costs >= 1, ties prefer the diagonal), and
+                # adding the template's own bases keeps every column's first-maximum tally, so
+                # the consensus does not move.  Most copies of a merged block are exact, which
+                # makes this the difference between O(k^2) and O(k) per copy.
+                units.append(template)
+                unit_ops.append([])
+                errors.append(0)
+                for col, base in enumerate(template):
+                    tallies[col][base] += 1
+                pos += k
+                continue
             res = MotifUtils._align_unit_to_window(template, window, max_indel, tol)
             if res is None or res.consumed == 0:
                 break

@@ -315,18 +315,26 @@ class TandemRepeatFinder:
         shortest = min(len(m1), len(m2))
         if max(0, r2.start - r1.end) > shortest + 1:
             return False
+        self._union_memo = None
+        key = (r1.chrom, min(r1.start, r2.start), max(r1.end, r2.end), max(1, shortest), min(r1.tier, r2.tier))
         try:
-            union = self._recompute_repeat(r1.chrom, min(r1.start, r2.start), max(r1.end, r2.end), max(1, shortest),
-                                           tier_hint=min(r1.tier, r2.tier))
+            union = self._recompute_repeat(*key[:4], tier_hint=key[4])
         except ValueError:
             return False
+        # _merge_repeats re-derives the same union whenever r1's motif is the shorter one; the
+        # alignment is a pure function of these arguments, so the record is handed over once.
+        self._union_memo = (key, union)
         if union.copies < self.min_copies:
             return False
         return union.mismatch_rate <= max(r1.mismatch_rate, r2.mismatch_rate, 0.01) + 0.2
 
     def _merge_repeats(self, r1: TandemRepeat, r2: TandemRepeat) -> TandemRepeat:
-        return self._recompute_repeat(r1.chrom, min(r1.start, r2.start), max(r1.end, r2.end),
-                                      len(r1.consensus_motif or r1.motif), tier_hint=min(r1.tier, r2.tier))
+        key = (r1.chrom, min(r1.start, r2.start), max(r1.end, r2.end),
+               len(r1.consensus_motif or r1.motif), min(r1.tier, r2.tier))
+        memo, self._union_memo = getattr(self, "_union_memo", None), None
+        if memo is not None and memo[0] == key:
+            return memo[1]
+        return self._recompute_repeat(*key[:4], tier_hint=key[4])
 
     def _refine_repeats(self, repeats: List[TandemRepeat]) -> List[TandemRepeat]:
         out: List[TandemRepeat] = []

@@ -89,3 +89,82 @@ def test_natural_sort_key_memo():
     for v in ("chr10", "chr2", "Chr2_random", None, "7", "scaffold_12_3"):
         assert _natural_sort_key(v) == _natural_sort_key_uncached(v)
     assert sorted(["chr10", "chr2", "chr1"], key=_natural_sort_key) == ["chr1", "chr2", "chr10"]
+
+
+def _mutated_tandem(rng, k, copies, rate):
+    motif = "".join("ACGT"[x] for x in rng.integers(0, 4, k))
+    out = []
+    for _ in range(copies):
+        unit = list(motif)
+        r = rng.random()
+        if r < rate:
+            unit[int(rng.integers(0, k))] = "ACGT"[int(rng.integers(0, 4))]
+        elif r < 1.5 * rate:
+            unit.insert(int(rng.integers(0, k + 1)), "ACGT"[int(rng.integers(0, 4))])
+        elif r < 2 * rate and k > 1:
+            del unit[int(rng.integers(0, k))]
+        out.append("".join(unit))
+    return motif, "".join(out)
+
+
+def test_exact_copy_fast_path_equals_dp_walk():
+    """align_repeat_region skips the banded DP for copies equal to the running consensus; the
+    summary (consensus, variations, error counts, consumed span) must not change."""
+    rng = np.random.default_rng(17)
+    checked = hits = 0
+    for trial in range(400):
+        k = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 9, 12, 20, 33]))
+        motif, body = _mutated_tandem(rng, k, int(rng.integers(2, 30)), float(rng.choice([0.0, 0.1, 0.3])))
+        left = "".join("ACGTN"[x] for x in rng.integers(0, 5, int(rng.integers(0, 40))))
+        right = "".join("ACGT"[x] for x in rng.integers(0, 4, int(rng.integers(0, 40))))
+        seq = left + body + right
+        start = len(left) + int(rng.integers(0, 3))
+        end = len(left) + len(body) - int(rng.integers(0, 3))
+        template = seq[start:start + k] if rng.random() < 0.8 else motif
+        for min_copies in (3, 1):
+            MotifUtils._EXACT_COPY_FAST_PATH = False
+            try:
+                want = MotifUtils.align_repeat_region(seq, start, end, template, 0.1, min_copies=min_copies)
+            finally:
+                MotifUtils._EXACT_COPY_FAST_PATH = True
+            got = MotifUtils.align_repeat_region(seq, start, end, template, 0.1, min_copies=min_copies)
+            assert got == want, (trial, seq, start, end, template)
+            checked += 1
+            hits += bool(want and want.copies > 3 and 0 in want.error_counts and any(want.error_counts))
+    assert checked == 800 and hits > 50   # mixed exact / inexact walks were exercised
+
+
+def test_merge_hands_over_the_union_record():
+    """_merge_adjacent_repeats re-uses the union derived by _should_merge_repeats when the
+    arguments coincide; same merged records as two independent derivations."""
+    rng = np.random.default_rng(23)
+    pieces, recs, pos = [], [], 0
+    for i in range(300):
+        gap = "".join("ACGT"[x] for x in rng.integers(0, 4, int(rng.integers(0, 6)) if i % 2 else 40))
+        k = int(rng.integers(1, 8))
+        motif, body = _mutated_tandem(rng, k, int(rng.integers(3, 12)), 0.0)
+        if i % 2 and recs:                       # a second block of the previous motif, after a short gap
+            motif = recs[-1].motif
+            k = len(motif)
+            body = motif * int(rng.integers(3, 9))
+        pieces.append(gap)
+        pos += len(gap)
+        recs.append(TandemRepeat(chrom="c", start=pos, end=pos + len(body), motif=motif, copies=len(body) / k,
+                                 length=len(body), tier=2, confidence=0.95, consensus_motif=motif))
+        pieces.append(body)
+        pos += len(body)
+    seq = "".join(pieces)
+
+    def finder():
+        f = TandemRepeatFinder("/dev/null")
+        f.sequences = {"c": seq}
+        return f
+
+    fast = finder()._merge_adjacent_repeats(list(recs))
+    plain = finder()
+    plain._merge_repeats = lambda r1, r2: plain._recompute_repeat(
+        r1.chrom, min(r1.start, r2.start), max(r1.end, r2.end), len(r1.consensus_motif or r1.motif),
+        tier_hint=min(r1.tier, r2.tier))
+    slow = plain._merge_adjacent_repeats(list(recs))
+    assert fast == slow and len(fast) < len(recs)
+    assert len({id(r) for r in fast}) == len(fast)
