@@ -265,6 +265,51 @@ def run_ours(args):
 
     extras = {}
     roof = None
+    if world > 1 and not args.skip_extras:
+        # ---- one contig, N GPUs: rank 0's FM index replicated over NVLink, the 10-mer batch split ----
+        # (SURVEY 8e / BASELINE "motif batches per GPU"): broadcast of BWT + Occ, then every rank answers
+        # its block of the batch and one all_gather returns all (sp, ep); device-timed, max over ranks.
+        from types import SimpleNamespace
+
+        from bwt_algorithm_b200 import sharding
+        from bwt_algorithm_b200.device_index import FMReplica
+
+        built = SimpleNamespace(n=n, occ_rate=128, bwt=step.bwt, occ=step.occ, totals=step.totals,
+                                row_of_code=step.row) if rank == 0 else None
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        fm = sharding.broadcast_fm(built, src=0, device=dev)
+        b1.record()
+        torch.cuda.synchronize()
+        bcast_ms = b0.elapsed_time(b1)
+        replica = FMReplica(device=dev, **fm)
+        nq_all = (1 << 22) * world
+        q_host = np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(7).integers(0, 4, (nq_all, 10), dtype=np.uint8)]
+        q_pats = torch.from_numpy(q_host).to(dev)
+        q_lens = torch.full((nq_all,), 10, dtype=torch.int32, device=dev)
+        sharding.sharded_search(replica.search_block, q_pats, q_lens)       # warm-up
+        qs = []
+        for _ in range(3):
+            flush.fill_(1)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            q_sp, q_ep = sharding.sharded_search(replica.search_block, q_pats, q_lens)
+            a1.record()
+            torch.cuda.synchronize()
+            qs.append(a0.elapsed_time(a1))
+        t = torch.tensor([statistics.median(qs), bcast_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        q_ms, bcast_ms = float(t[0].item()), float(t[1].item())
+        found = int((q_sp >= 0).sum().item())
+        extras["fm_sharded_10mers"] = {
+            "queries": nq_all, "ms": round(q_ms, 4), "queries_per_s": round(nq_all / (q_ms * 1e-3), 1),
+            "found": found, "index_broadcast_ms": round(bcast_ms, 4),
+            "index_broadcast_bytes": int(fm["bwt"].numel() + fm["occ"].numel() * 4),
+            "note": "rank 0's chr21-sized index broadcast over NCCL, batch split in equal blocks, "
+                    "all_gather of (sp, ep) inside the timed region"}
+        del replica, fm, q_pats, q_lens, q_sp, q_ep
     if rank == 0 and args.skip_extras:
         peak, peak_src = measured_peak()
     if rank == 0 and not args.skip_extras:

@@ -24,7 +24,80 @@ def _torch():
     return _lib.require_cuda()
 
 
-class DeviceIndex:
+class _FMSearch:
+    """Rank / backward search over (bwt, occ, C) held on one device; shared by the full
+    ``DeviceIndex`` and the search-only ``FMReplica``."""
+
+    # ------------------------------------------------------------------ a8 / a9
+    def search_device(self, d_pats, stride: int, d_lens, nq: int):
+        torch, L = self.torch, _lib.lib()
+        with torch.cuda.device(self.device):
+            sp = torch.empty(nq, dtype=torch.int32, device=self.device)
+            ep = torch.empty(nq, dtype=torch.int32, device=self.device)
+            _lib.check(L.bwtk_bsearch_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
+                                            self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
+                                            self.d_row.data_ptr(), self.n, _lib.ptr(d_pats), stride,
+                                            d_lens.data_ptr(), nq, sp.data_ptr(), ep.data_ptr(),
+                                            _lib.stream_ptr()), "bsearch_batch")
+        return sp, ep
+
+    def search_block(self, d_pats, d_lens):
+        """(sp, ep) device tensors for a block of a padded query matrix (uint8[nq, stride],
+        int32[nq]); the callable ``sharding.sharded_search`` expects."""
+        nq = int(d_lens.shape[0])
+        d_pats = d_pats.contiguous()
+        stride = int(d_pats.shape[1]) if d_pats.dim() == 2 and nq else 1
+        return self.search_device(d_pats, stride, d_lens.contiguous(), nq)
+
+    def backward_search_batch(self, patterns: Sequence) -> Tuple[np.ndarray, np.ndarray]:
+        """Inclusive (sp, ep) for every pattern (bytes/str); (-1,-1) when absent."""
+        torch = self.torch
+        nq = len(patterns)
+        if nq == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
+        bs = [p.encode("utf-8") if isinstance(p, str) else bytes(p) for p in patterns]
+        stride = max(1, max(len(b) for b in bs))
+        mat = np.zeros((nq, stride), np.uint8)
+        lens = np.zeros(nq, np.int32)
+        for i, b in enumerate(bs):
+            lens[i] = len(b)
+            if b:
+                mat[i, : len(b)] = np.frombuffer(b, np.uint8)
+        d_p = torch.from_numpy(mat).to(self.device)
+        d_l = torch.from_numpy(lens).to(self.device)
+        sp, ep = self.search_device(d_p, stride, d_l, nq)
+        return sp.cpu().numpy(), ep.cpu().numpy()
+
+    def motif_sweep(self, kmax: int = 10):
+        """(sp, ep) device tensors for every ACGT motif of length 1..kmax, index
+        (4^k-4)/3 + base-4 value (first character most significant)."""
+        torch, L = self.torch, _lib.lib()
+        total = (4 ** (kmax + 1) - 4) // 3
+        with torch.cuda.device(self.device):
+            sp = torch.empty(total, dtype=torch.int32, device=self.device)
+            ep = torch.empty(total, dtype=torch.int32, device=self.device)
+            _lib.check(L.bwtk_bsearch_motif_sweep(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
+                                                  self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
+                                                  self.d_row.data_ptr(), self.n, kmax, sp.data_ptr(),
+                                                  ep.data_ptr(), _lib.stream_ptr()), "motif_sweep")
+        return sp, ep
+
+    def rank_batch(self, codes: Sequence[int], positions: Sequence[int]) -> np.ndarray:
+        torch, L = self.torch, _lib.lib()
+        nq = len(codes)
+        if nq == 0:
+            return np.zeros(0, np.int64)
+        with torch.cuda.device(self.device):
+            d_c = torch.tensor(list(codes), dtype=torch.int32, device=self.device)
+            d_p = torch.tensor(list(positions), dtype=torch.int64, device=self.device)
+            out = torch.empty(nq, dtype=torch.int64, device=self.device)
+            _lib.check(L.bwtk_rank_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
+                                         self.occ_rate, self.d_row.data_ptr(), self.n, d_c.data_ptr(),
+                                         d_p.data_ptr(), nq, out.data_ptr(), _lib.stream_ptr()), "rank_batch")
+        return out.cpu().numpy()
+
+
+class DeviceIndex(_FMSearch):
     def __init__(self, text, occ_rate: int = 128, device=None, build_kmer: bool = True,
                  text_is_device: bool = False, build_lcp: bool = False, build_isa: bool = False):
         torch = _torch()
@@ -132,62 +205,24 @@ class DeviceIndex:
                                                 ws.data_ptr(), wsb, _lib.stream_ptr()), "lcp_build")
         return self._lcp
 
-    # ------------------------------------------------------------------ a8 / a9
-    def search_device(self, d_pats, stride: int, d_lens, nq: int):
-        torch, L = self.torch, _lib.lib()
-        with torch.cuda.device(self.device):
-            sp = torch.empty(nq, dtype=torch.int32, device=self.device)
-            ep = torch.empty(nq, dtype=torch.int32, device=self.device)
-            _lib.check(L.bwtk_bsearch_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
-                                            self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
-                                            self.d_row.data_ptr(), self.n, _lib.ptr(d_pats), stride,
-                                            d_lens.data_ptr(), nq, sp.data_ptr(), ep.data_ptr(),
-                                            _lib.stream_ptr()), "bsearch_batch")
-        return sp, ep
 
-    def backward_search_batch(self, patterns: Sequence) -> Tuple[np.ndarray, np.ndarray]:
-        """Inclusive (sp, ep) for every pattern (bytes/str); (-1,-1) when absent."""
-        torch = self.torch
-        nq = len(patterns)
-        if nq == 0:
-            return np.zeros(0, np.int32), np.zeros(0, np.int32)
-        bs = [p.encode("utf-8") if isinstance(p, str) else bytes(p) for p in patterns]
-        stride = max(1, max(len(b) for b in bs))
-        mat = np.zeros((nq, stride), np.uint8)
-        lens = np.zeros(nq, np.int32)
-        for i, b in enumerate(bs):
-            lens[i] = len(b)
-            if b:
-                mat[i, : len(b)] = np.frombuffer(b, np.uint8)
-        d_p = torch.from_numpy(mat).to(self.device)
-        d_l = torch.from_numpy(lens).to(self.device)
-        sp, ep = self.search_device(d_p, stride, d_l, nq)
-        return sp.cpu().numpy(), ep.cpu().numpy()
+class FMReplica(_FMSearch):
+    """Search-only copy of a contig's FM index (BWT bytes, Occ checkpoints, C array) on
+    another GPU: what ``sharding.broadcast_fm`` hands to the ranks that did not build the
+    index, so that a motif batch can be split across the GPUs of a box."""
 
-    def motif_sweep(self, kmax: int = 10):
-        """(sp, ep) device tensors for every ACGT motif of length 1..kmax, index
-        (4^k-4)/3 + base-4 value (first character most significant)."""
-        torch, L = self.torch, _lib.lib()
-        total = (4 ** (kmax + 1) - 4) // 3
-        with torch.cuda.device(self.device):
-            sp = torch.empty(total, dtype=torch.int32, device=self.device)
-            ep = torch.empty(total, dtype=torch.int32, device=self.device)
-            _lib.check(L.bwtk_bsearch_motif_sweep(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
-                                                  self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
-                                                  self.d_row.data_ptr(), self.n, kmax, sp.data_ptr(),
-                                                  ep.data_ptr(), _lib.stream_ptr()), "motif_sweep")
-        return sp, ep
-
-    def rank_batch(self, codes: Sequence[int], positions: Sequence[int]) -> np.ndarray:
-        torch, L = self.torch, _lib.lib()
-        nq = len(codes)
-        if nq == 0:
-            return np.zeros(0, np.int64)
-        with torch.cuda.device(self.device):
-            d_c = torch.tensor(list(codes), dtype=torch.int32, device=self.device)
-            d_p = torch.tensor(list(positions), dtype=torch.int64, device=self.device)
-            out = torch.empty(nq, dtype=torch.int64, device=self.device)
-            _lib.check(L.bwtk_rank_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
-                                         self.occ_rate, self.d_row.data_ptr(), self.n, d_c.data_ptr(),
-                                         d_p.data_ptr(), nq, out.data_ptr(), _lib.stream_ptr()), "rank_batch")
-        return out.cpu().numpy()
+    def __init__(self, bwt, occ, totals, row, n: int, occ_rate: int, device=None):
+        torch = _torch()
+        self.torch = torch
+        self.device = torch.device(device if device is not None else bwt.device)
+        self.n, self.occ_rate = int(n), int(occ_rate)
+        self.bwt = bwt.to(self.device)
+        self.occ = occ.to(self.device)
+        totals = np.ascontiguousarray(totals, np.int64)
+        self.totals = totals
+        self.counts = np.concatenate(([0], np.cumsum(totals)[:-1])).astype(np.int64)
+        self.row_of_code = np.ascontiguousarray(row, np.int32)
+        self.codes = [b for b in range(256) if totals[b] > 0]
+        self.d_C = torch.from_numpy(self.counts).to(self.device)
+        self.d_tot = torch.from_numpy(totals).to(self.device)
+        self.d_row = torch.from_numpy(self.row_of_code).to(self.device)

@@ -99,3 +99,80 @@ def gather_rows(rows: np.ndarray, contig_ids: np.ndarray, group=None, device=Non
     parts = [b[:c].cpu().numpy() for b, c in zip(blocks, counts)]
     merged = np.concatenate(parts, axis=0) if parts else np.zeros((0, REC_W + 1), np.int32)
     return merged[:, :REC_W].copy(), merged[:, REC_W].copy()
+
+
+# ---------------------------------------------------------------------------
+# one contig, many GPUs: the motif batch is split, the index is replicated
+# ---------------------------------------------------------------------------
+def split_range(count: int, parts: int) -> List[Tuple[int, int]]:
+    """[lo, hi) of each of `parts` equal blocks of ceil(count/parts) items (the last ones may
+    be short or empty) -- equal blocks keep the result gather one fixed-size all_gather."""
+    parts = max(1, int(parts))
+    block = -(-int(count) // parts) if count > 0 else 0
+    return [(min(count, r * block), min(count, (r + 1) * block)) for r in range(parts)]
+
+
+def broadcast_fm(index, src: int = 0, group=None, device=None) -> dict:
+    """Replicates the search side of a contig's FM index -- BWT bytes, Occ checkpoints, byte
+    totals and the byte->row map (bwt.py:266-326) -- from rank `src` to every rank: one small
+    object broadcast for the shapes, then the two arrays (NCCL over NVLink when the ranks own
+    GPUs; 1.25 B/base for an ACGT$ contig at the default checkpoint rate).  `index` is a
+    ``DeviceIndex`` (or any object with bwt/occ/totals/row_of_code/n/occ_rate) on `src` and
+    ignored elsewhere.  Returns the keyword arguments of ``FMReplica``."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    meta = [None]
+    if rank == src:
+        meta = [dict(n=int(index.n), occ_rate=int(index.occ_rate), occ_shape=tuple(index.occ.shape),
+                     totals=np.asarray(index.totals, np.int64).tolist(),
+                     row=np.asarray(index.row_of_code, np.int32).tolist())]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    m = meta[0]
+    if rank == src:
+        bwt = torch.as_tensor(index.bwt).to(dev).contiguous()
+        occ = torch.as_tensor(index.occ).to(dev).contiguous()
+    else:
+        bwt = torch.empty(m["n"], dtype=torch.uint8, device=dev)
+        occ = torch.empty(m["occ_shape"], dtype=torch.int32, device=dev)
+    if m["n"]:
+        dist.broadcast(bwt, src=src, group=group)
+    if occ.numel():
+        dist.broadcast(occ, src=src, group=group)
+    return dict(bwt=bwt, occ=occ, totals=np.array(m["totals"], np.int64), row=np.array(m["row"], np.int32),
+                n=m["n"], occ_rate=m["occ_rate"])
+
+
+def sharded_search(search: Callable, patterns, lengths, group=None):
+    """Backward search of one query batch split over the ranks of `group`.
+
+    Every rank passes the same `patterns` (uint8[nq, stride] tensor) and `lengths` (int32[nq])
+    on its own device and a `search(patterns_block, lengths_block) -> (sp, ep)` callable bound to
+    its replica of the index (``FMReplica.search_block``).  Rank r answers block r of
+    ``split_range(nq, world)``; one all_gather of fixed-size (2, block) int32 tiles returns the
+    inclusive (sp, ep) of every query, in query order, on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    nq = int(lengths.shape[0])
+    dev = lengths.device
+    if nq == 0:
+        empty = torch.zeros(0, dtype=torch.int32, device=dev)
+        return empty, empty.clone()
+    spans = split_range(nq, world)
+    lo, hi = spans[rank]
+    block = spans[0][1] - spans[0][0]
+    tile = torch.full((2, block), -1, dtype=torch.int32, device=dev)
+    if hi > lo:
+        sp, ep = search(patterns[lo:hi], lengths[lo:hi])
+        tile[0, : hi - lo] = sp
+        tile[1, : hi - lo] = ep
+    tiles = [torch.empty_like(tile) for _ in range(world)]
+    dist.all_gather(tiles, tile, group=group)
+    sp_all = torch.cat([t[0, : b - a] for t, (a, b) in zip(tiles, spans)])
+    ep_all = torch.cat([t[1, : b - a] for t, (a, b) in zip(tiles, spans)])
+    return sp_all, ep_all

@@ -118,6 +118,84 @@ def test_two_rank_record_gather_gloo(tmp_path):
     assert "GATHER_OK" in res.stdout
 
 
+_SEARCH_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+import bwt_algorithm_b200
+from bwt_algorithm_b200.sharding import broadcast_fm, sharded_search, split_range
+from oracle import oracle as orc
+from tests.util import gen_contig
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+assert split_range(10, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)] and split_range(2, 4)[2:] == [(2, 2), (2, 2)]
+assert split_range(0, 3) == [(0, 0)] * 3
+
+
+class Built:                      # what rank 0's DeviceIndex exposes, filled from the oracle
+    def __init__(self, text):
+        oi = orc.OracleIndex(text)
+        codes = [c for c in range(256) if oi.totals[c] > 0]
+        self.n, self.occ_rate, self.totals = oi.n, 128, oi.totals
+        self.row_of_code = np.full(256, -1, np.int32)
+        self.row_of_code[codes] = np.arange(len(codes))
+        self.bwt = torch.from_numpy(oi.bwt.copy())
+        self.occ = torch.from_numpy(np.ascontiguousarray(oi.occ_matrix()[codes]))
+
+
+text = gen_contig(30_000, 77).tobytes() + b"$"
+fm = broadcast_fm(Built(text) if rank == 0 else None, src=0)
+assert fm["n"] == len(text) and fm["bwt"].shape == (len(text),) and fm["occ"].shape[0] == 5
+
+# a CPU search bound to the replica arrays only (the GPU ranks bind FMReplica.search_block)
+totals = fm["totals"]
+counts = np.concatenate(([0], np.cumsum(totals)[:-1])).astype(np.int64)
+occ256 = np.zeros((256, fm["occ"].shape[1]), np.int32)
+for code in range(256):
+    if fm["row"][code] >= 0:
+        occ256[code] = fm["occ"][fm["row"][code]].numpy()
+bwt = fm["bwt"].numpy()
+
+
+def search(pats, lens):
+    pats = np.ascontiguousarray(pats.numpy()); lens = np.ascontiguousarray(lens.numpy())
+    sp = np.empty(lens.size, np.int64); ep = np.empty(lens.size, np.int64)
+    orc.lib().orc_backward_search_batch(orc._ptr(bwt), fm["n"], fm["occ_rate"], orc._ptr(occ256), occ256.shape[1],
+                                        orc._ptr(totals), orc._ptr(counts), orc._ptr(pats), pats.shape[1],
+                                        orc._ptr(lens), lens.size, orc._ptr(sp), orc._ptr(ep))
+    return torch.from_numpy(sp.astype(np.int32)), torch.from_numpy(ep.astype(np.int32))
+
+
+rng = np.random.default_rng(5)
+for nq in (0, 1, 2, 3, 1001):
+    lens = rng.integers(0, 11, nq).astype(np.int32)
+    pats = np.frombuffer(b"ACGTN", np.uint8)[rng.integers(0, 5, (nq, 10))]
+    sp, ep = sharded_search(search, torch.from_numpy(pats), torch.from_numpy(lens))
+    full = orc.OracleIndex(text)
+    wsp, wep = full.backward_search_batch(pats, lens) if nq else (np.zeros(0), np.zeros(0))
+    assert np.array_equal(sp.numpy(), wsp) and np.array_equal(ep.numpy(), wep), nq
+    if nq > 100:
+        assert (sp.numpy() >= 0).sum() > 100 and (sp.numpy() < 0).sum() > 10
+dist.barrier()
+if rank == 0:
+    print("SEARCH_OK", flush=True)
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharded_search_gloo(tmp_path):
+    """One contig, two ranks: the FM arrays are broadcast from the rank that built them, the query batch is
+    split, and every rank ends up with the (sp, ep) of every query in query order."""
+    script = tmp_path / "worker.py"
+    script.write_text(_SEARCH_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519", CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29519", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "SEARCH_OK" in res.stdout
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs next to ours) on a tiny sample."""
     import json
