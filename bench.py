@@ -276,13 +276,14 @@ def run_ours(args):
 
         built = SimpleNamespace(n=n, occ_rate=128, bwt=step.bwt, occ=step.occ, totals=step.totals,
                                 row_of_code=step.row) if rank == 0 else None
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        fm = sharding.broadcast_fm(built, src=0, device=dev)
-        b1.record()
-        torch.cuda.synchronize()
-        bcast_ms = b0.elapsed_time(b1)
+        for _ in range(2):          # the first broadcast also sets up NCCL's broadcast channels
+            barrier()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            fm = sharding.broadcast_fm(built, src=0, device=dev)
+            b1.record()
+            torch.cuda.synchronize()
+            bcast_ms = b0.elapsed_time(b1)
         replica = FMReplica(device=dev, **fm)
         nq_all = (1 << 22) * world
         q_host = np.frombuffer(b"ACGT", np.uint8)[np.random.default_rng(7).integers(0, 4, (nq_all, 10), dtype=np.uint8)]

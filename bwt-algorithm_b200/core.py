@@ -81,7 +81,8 @@ class BWTCore:
     BASE_TO_BITS = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 0}
     BITS_TO_BASE = {0: "A", 1: "C", 2: "G", 3: "T"}
 
-    def __init__(self, text: str, sa_sample_rate: int = 32, occ_sample_rate: int = 128, device=None):
+    def __init__(self, text: str, sa_sample_rate: int = 32, occ_sample_rate: int = 128, device=None,
+                 _index: DeviceIndex = None):
         self.text: str = text
         self.n = len(text)
         self.sa_sample_rate = sa_sample_rate
@@ -89,7 +90,7 @@ class BWTCore:
         raw = text.encode("utf-8")
         self._host: Dict[str, object] = {"text_arr": np.frombuffer(raw, dtype=np.uint8)}
         # one H2D copy of the text, then everything is built in HBM
-        self._dev = DeviceIndex(raw, occ_rate=int(occ_sample_rate), device=device)
+        self._dev = _index if _index is not None else DeviceIndex(raw, occ_rate=int(occ_sample_rate), device=device)
         self.alphabet = sorted(set(text))
         self.char_to_code = {c: ord(c) for c in self.alphabet}
         self.code_to_char = {ord(c): c for c in self.alphabet}
@@ -98,6 +99,18 @@ class BWTCore:
         self.char_counts = {c: int(cnt[ord(c)]) if ord(c) < 256 else 0 for c in self.alphabet}
         self.char_counts_code = {ord(k): v for k, v in self.char_counts.items()}
         self.char_totals_code = {ord(k): v for k, v in self.char_totals.items()}
+
+    # ---- persistence (no counterpart in the reference) -----------
+    def save_index(self, path, with_lcp: bool = True) -> None:
+        """Stores the device index (text, SA, BWT, Occ, C, optionally LCP) in one .npz file."""
+        self.device_index.save(path, with_lcp=with_lcp)
+
+    @classmethod
+    def load_index(cls, path, sa_sample_rate: int = 32, device=None) -> "BWTCore":
+        """A BWTCore over a stored index: the arrays are uploaded, nothing is sorted again."""
+        ix = DeviceIndex.load(path, device=device)
+        text = ix.text.cpu().numpy().tobytes().decode("utf-8")
+        return cls(text, sa_sample_rate, ix.occ_rate, device=device, _index=ix)
 
     # ---- lazily materialised NumPy attributes ------------------------------
     def _lazy(self, name, make):

@@ -145,26 +145,75 @@ class DeviceIndex(_FMSearch):
                     _lib.check(rc, "index_build")
                     break
                 del ws
-            self.totals = totals
-            counts = np.zeros(256, np.int64)
-            cum = 0
-            for b in range(256):
-                counts[b] = cum
-                cum += int(totals[b])
-            self.counts = counts
-            codes = [b for b in range(256) if totals[b] > 0]
-            self.codes = codes
-            self.row_of_code = row
-            self.occ = self.occ[: max(len(codes), 1)]
-            self.d_C = torch.from_numpy(counts).to(self.device)
-            self.d_tot = torch.from_numpy(totals).to(self.device)
-            self.d_row = torch.from_numpy(row).to(self.device)
+            self._set_alphabet(totals, row)
             # a2: 8-mer index
             self.kmer_off = None
             self.kmer_pos = None
             self.kmer_count = 0
             if build_kmer:
                 self.build_kmer()
+
+    def _set_alphabet(self, totals: np.ndarray, row: np.ndarray) -> None:
+        """Byte totals and byte->Occ-row map -> C array, code list and their device copies."""
+        torch = self.torch
+        self.totals = totals
+        counts = np.zeros(256, np.int64)
+        cum = 0
+        for b in range(256):
+            counts[b] = cum
+            cum += int(totals[b])
+        self.counts = counts
+        codes = [b for b in range(256) if totals[b] > 0]
+        self.codes = codes
+        self.row_of_code = row
+        self.occ = self.occ[: max(len(codes), 1)]
+        self.d_C = torch.from_numpy(counts).to(self.device)
+        self.d_tot = torch.from_numpy(totals).to(self.device)
+        self.d_row = torch.from_numpy(row).to(self.device)
+
+    # ------------------------------------------------------------------ persistence (SURVEY 8f-4)
+    _FORMAT = 1
+
+    def save(self, path, with_lcp: bool = True) -> None:
+        """Writes the index arrays to one uncompressed ``.npz`` (text, SA, BWT, Occ, byte totals,
+        row map and, unless declined, LCP) so that later scans of the same contig skip
+        construction.  The reference has no counterpart; the arrays are the ones of bwt.py:106-136."""
+        arrays = dict(format=np.int64(self._FORMAT), occ_rate=np.int64(self.occ_rate),
+                      text=self.text.cpu().numpy(), sa=self.sa.cpu().numpy(), bwt=self.bwt.cpu().numpy(),
+                      occ=self.occ.cpu().numpy(), totals=self.totals, row=self.row_of_code)
+        if with_lcp:
+            arrays["lcp"] = self.lcp.cpu().numpy()
+        with open(path, "wb") as fh:
+            np.savez(fh, **arrays)
+
+    @classmethod
+    def load(cls, path, device=None, build_kmer: bool = True) -> "DeviceIndex":
+        """The inverse of ``save``: uploads the stored arrays (no suffix sorting); the 8-mer table
+        is rebuilt from the text (one counting pass) and ISA is not kept."""
+        torch = _torch()
+        with np.load(path) as z:
+            if int(z["format"]) != cls._FORMAT:
+                raise ValueError(f"{path}: index format {int(z['format'])}, expected {cls._FORMAT}")
+            host = {k: z[k] for k in z.files}
+        self = cls.__new__(cls)
+        self.torch = torch
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.occ_rate = int(host["occ_rate"])
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        self.text, self.sa, self.bwt, self.occ = up(host["text"]), up(host["sa"]), up(host["bwt"]), up(host["occ"])
+        n = self.n = int(self.text.numel())
+        if not (self.sa.numel() == n and self.bwt.numel() == n and self.sa.dtype == torch.int32):
+            raise ValueError(f"{path}: array sizes do not agree")
+        self.isa = None
+        self._lcp = up(host["lcp"]) if "lcp" in host else None
+        self.sa_stats = np.zeros(8, np.int64)
+        self.ncp = (n // self.occ_rate + 1 + (1 if n % self.occ_rate else 0)) if n else 0
+        self._set_alphabet(host["totals"].astype(np.int64), host["row"].astype(np.int32))
+        self.kmer_off = self.kmer_pos = None
+        self.kmer_count = 0
+        if build_kmer:
+            self.build_kmer()
+        return self
 
     # ------------------------------------------------------------------ a2
     def build_kmer(self):

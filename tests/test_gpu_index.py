@@ -258,3 +258,47 @@ def test_kernel_transfers_roundtrip():
     pageable = torch.zeros(64, dtype=torch.uint8)
     dev = torch.zeros(64, dtype=torch.uint8, device="cuda")
     assert L.bwtk_upload_text(pageable.data_ptr(), dev.data_ptr(), 64, _lib.stream_ptr()) != 0   # not pinned
+
+
+@pytest.mark.parametrize("name,text", [(n, t) for n, t in text_cases() if n in
+                                       ("one_sentinel", "n129", "N_runs", "binaryish", "planted_20000_N")])
+def test_index_save_load_round_trip(DeviceIndex, oracle, tmp_path, name, text):
+    """A stored index comes back with the same arrays and answers the same searches."""
+    ix = DeviceIndex(text, build_lcp=True)
+    path = tmp_path / f"{name}.npz"
+    ix.save(path)
+    back = DeviceIndex.load(path)
+    oi = oracle.OracleIndex(text)
+    assert back.n == ix.n == len(text) and back.occ_rate == ix.occ_rate
+    for attr in ("text", "sa", "bwt", "occ", "lcp"):
+        assert np.array_equal(getattr(back, attr).cpu().numpy(), getattr(ix, attr).cpu().numpy()), attr
+    assert np.array_equal(back.sa.cpu().numpy(), oi.sa) and np.array_equal(back.lcp.cpu().numpy(), oi.lcp())
+    assert np.array_equal(back.totals, ix.totals) and np.array_equal(back.counts, ix.counts)
+    assert back.codes == ix.codes and back.kmer_count == ix.kmer_count
+    assert np.array_equal(back.kmer_off.cpu().numpy(), ix.kmer_off.cpu().numpy())
+    pats = [b"A", b"ACG", b"GATTACA", b"NN", b"", b"TTTTTTTTTT", bytes([text[0]])]
+    sp, ep = back.backward_search_batch(pats)
+    for p, a, b in zip(pats, sp, ep):
+        assert (int(a), int(b)) == oi.backward_search(p), p
+    # without LCP: rebuilt on demand from the stored SA
+    ix.save(path, with_lcp=False)
+    lazy = DeviceIndex.load(path, build_kmer=False)
+    assert lazy._lcp is None and np.array_equal(lazy.lcp.cpu().numpy(), oi.lcp())
+
+
+def test_bwtcore_load_index_matches_fresh_build(tmp_path):
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200.bwt import BWTCore
+
+    text = gen_contig(30_000, 4).tobytes().decode() + "$"
+    fresh = BWTCore(text)
+    fresh.save_index(tmp_path / "c.npz")
+    back = BWTCore.load_index(tmp_path / "c.npz")
+    assert back.text == fresh.text and back.alphabet == fresh.alphabet and back.char_counts == fresh.char_counts
+    assert np.array_equal(back.suffix_array, fresh.suffix_array) and np.array_equal(back.bwt_arr, fresh.bwt_arr)
+    for code in fresh.occ_checkpoints:
+        assert np.array_equal(back.occ_checkpoints[code], fresh.occ_checkpoints[code])
+    for pat in ("ACGT", "TTT", "GATTACA", "", "N"):
+        assert back.backward_search(pat) == fresh.backward_search(pat)
+        assert back.locate_positions(pat) == fresh.locate_positions(pat)
+    assert back.get_kmer_positions("ACGTACGT") == fresh.get_kmer_positions("ACGTACGT")
