@@ -9,7 +9,9 @@ max_mm_per_copy, aux0, aux1) on the host.  The float fields of a
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+import threading
+import weakref
+from typing import List, Optional, Tuple
 
 import numpy as np
 
@@ -56,17 +58,55 @@ def _run_rows(call, ws_bytes: int, device, cap0: int) -> np.ndarray:
     raise _lib.BwtkError("record buffer kept overflowing")
 
 
+class _PinnedPool:
+    """Pinned host blocks for detector rows, lent out as NumPy arrays and taken back when the
+    array (and every view of it) has been garbage-collected.
+
+    torch's caching host allocator reuses a block only inside its power-of-two size class, and
+    the first block of a class costs a cudaHostAlloc of 100+ ms: the strict scans of a genome's
+    contigs (425, 292, 267, 174, 80 MB of rows ...) hit four classes.  Here any free block that
+    is large enough serves a request, so one block per rows-in-flight is allocated for the
+    largest contig and then reused by every smaller one."""
+
+    KEEP_FREE = 3
+
+    def __init__(self):
+        self._free: List = []
+        self._lock = threading.Lock()
+
+    def _give(self, block) -> None:
+        with self._lock:
+            self._free.append(block)
+            if len(self._free) > self.KEEP_FREE:
+                self._free.remove(min(self._free, key=lambda b: b.numel()))
+
+    def lend(self, torch, d_rows) -> np.ndarray:
+        nbytes = d_rows.numel() * d_rows.element_size()
+        with self._lock:
+            fits = [b for b in self._free if b.numel() >= nbytes]
+            block = min(fits, key=lambda b: b.numel()) if fits else None
+            if block is not None:
+                self._free.remove(block)
+        if block is None:
+            block = torch.empty(1 << max(nbytes - 1, 1).bit_length(), dtype=torch.uint8, pin_memory=True)
+        h = block[:nbytes].view(d_rows.dtype).view(d_rows.shape)
+        h.copy_(d_rows, non_blocking=True)
+        torch.cuda.current_stream(d_rows.device).synchronize()
+        out = h.numpy()               # views of `out` keep `out` alive, `out` keeps the storage alive
+        weakref.finalize(out, self._give, block)
+        return out
+
+
+_pinned_rows = _PinnedPool()
+
+
 def _rows_to_host(torch, d_rows) -> np.ndarray:
     """Device rows -> NumPy.  Large results (a chr21-sized strict scan returns 80 MB) land in pinned
-    memory from torch's caching host allocator: the download runs at PCIe speed instead of the
-    ~2 GB/s of a copy into freshly allocated pageable memory, and the array keeps its block alive.
-    (The first block of a size class costs a cudaHostAlloc, ~2 ms per MB; it is reused afterwards.)"""
+    memory (``_PinnedPool``): the download runs at PCIe speed instead of the ~2 GB/s of a copy into
+    freshly allocated pageable memory, and the array owns its block until it is collected."""
     if d_rows.numel() * d_rows.element_size() >= (8 << 20):
         try:
-            h = torch.empty(d_rows.shape, dtype=d_rows.dtype, pin_memory=True)
-            h.copy_(d_rows, non_blocking=True)
-            torch.cuda.current_stream(d_rows.device).synchronize()
-            return h.numpy()
+            return _pinned_rows.lend(torch, d_rows)
         except RuntimeError:
             pass   # pinned memory exhausted: fall through to the pageable copy
     return d_rows.cpu().numpy()

@@ -156,3 +156,38 @@ def test_strict_rows_with_mismatches(detect, oracle, params):
     got = detect.strict_rows(text, *params)
     assert np.array_equal(got, want), f"{len(got)} vs {len(want)}"
     assert len(want) > 0
+
+
+def test_pinned_row_pool_reuses_any_large_enough_block(detect):
+    """Detector rows of >= 8 MB land in pinned blocks that return to the pool when the array and its
+    views are gone; a smaller download then reuses the larger block instead of allocating its class."""
+    import gc
+
+    import torch
+
+    pool = detect._PinnedPool()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    big = torch.arange(3_000_000 * 8, dtype=torch.int32, device=dev).reshape(-1, 8)
+    small = big[:400_000] * 3
+    a = pool.lend(torch, big)
+    assert a.shape == (3_000_000, 8) and a.dtype == np.int32 and np.array_equal(a, big.cpu().numpy())
+    base_a = a.__array_interface__["data"][0]
+    b = pool.lend(torch, small)                     # `a` is alive: a second block
+    assert b.__array_interface__["data"][0] != base_a and np.array_equal(b, small.cpu().numpy())
+    view = a[10:20, :4]
+    del a
+    gc.collect()
+    assert len(pool._free) == 0                     # a view keeps the block on loan
+    assert np.array_equal(view, big[10:20, :4].cpu().numpy())
+    del view
+    gc.collect()
+    assert len(pool._free) == 1
+    c = pool.lend(torch, small)                     # served by the big block
+    assert c.__array_interface__["data"][0] == base_a and np.array_equal(c, small.cpu().numpy())
+    assert np.array_equal(b, small.cpu().numpy())   # the other loan is untouched
+    del b, c
+    gc.collect()
+    assert len(pool._free) == 2
+    # the public path goes through the module's pool
+    rows = detect._rows_to_host(torch, big)
+    assert np.array_equal(rows, big.cpu().numpy())
