@@ -10,6 +10,7 @@ with the same expression order so derived floats match bit for bit
 """
 from __future__ import annotations
 
+import functools
 import math
 from collections import Counter
 from typing import Dict, Iterator, List, Optional, Tuple
@@ -24,6 +25,16 @@ _TRANSITIONS = {("A", "G"), ("G", "A"), ("C", "T"), ("T", "C")}
 
 def _rotations(s: str) -> List[str]:
     return [s[i:] + s[:i] for i in range(len(s))]
+
+
+def _canonical_stranded(motif) -> Tuple[str, str]:
+    """bwt.py:700-727: the smaller of the least rotation of the motif and of its reverse complement."""
+    fwd = min(_rotations(motif))
+    rev = min(_rotations("".join(_COMPLEMENT.get(b, b) for b in reversed(motif))))
+    return (fwd, "+") if fwd <= rev else (rev, "-")
+
+
+_canonical_stranded_cached = functools.lru_cache(maxsize=1 << 16)(_canonical_stranded)
 
 
 class MotifUtils:
@@ -42,9 +53,9 @@ class MotifUtils:
     def get_canonical_motif_stranded(motif: str) -> Tuple[str, str]:
         if not motif:
             return motif, "+"
-        fwd = min(_rotations(motif))
-        rev = min(_rotations(MotifUtils.reverse_complement(motif)))
-        return (fwd, "+") if fwd <= rev else (rev, "-")
+        if type(motif) is str:          # the post-processing chain asks for the same few motifs millions of times
+            return _canonical_stranded_cached(motif)
+        return _canonical_stranded(motif)
 
     @staticmethod
     def is_primitive_motif(motif: str) -> bool:

@@ -168,3 +168,21 @@ def test_merge_hands_over_the_union_record():
     slow = plain._merge_adjacent_repeats(list(recs))
     assert fast == slow and len(fast) < len(recs)
     assert len({id(r) for r in fast}) == len(fast)
+
+
+def test_canonical_motif_memo_equals_direct_form():
+    from bwt_algorithm_b200.motifs import _canonical_stranded
+
+    rng = np.random.default_rng(2)
+    motifs = ["", "A", "T", "AC", "GT", "ACGT", "TTAGGG", "CCCTAA", "NNA", "acgt", "AXT"]
+    motifs += ["".join("ACGTN"[x] for x in rng.integers(0, 5, int(rng.integers(1, 40)))) for _ in range(300)]
+    for m in motifs + motifs:                      # second round is served from the cache
+        got = MotifUtils.get_canonical_motif_stranded(m)
+        if m:
+            assert got == _canonical_stranded(m), m
+            fwd = min(m[i:] + m[:i] for i in range(len(m)))
+            rc = MotifUtils.reverse_complement(m)
+            rev = min(rc[i:] + rc[:i] for i in range(len(rc)))
+            assert got == ((fwd, "+") if fwd <= rev else (rev, "-")), m
+        else:
+            assert got == ("", "+")
