@@ -186,3 +186,42 @@ def test_canonical_motif_memo_equals_direct_form():
             assert got == ((fwd, "+") if fwd <= rev else (rev, "-")), m
         else:
             assert got == ("", "+")
+
+
+def test_postprocessing_chain_equals_reference_golden():
+    """tests/golden/chain_60k.json (oracle/gen_chain_golden.py): the unmodified reference's chain on the 3 166
+    strict-scan calls of a 60 kb planted contig -- stage counts, every field of every surviving record
+    (digest of the dataclass tuples, before and after the final filter) and the BED lines."""
+    import dataclasses
+    import hashlib
+    import json
+    import os
+
+    from tests.util import gen_contig
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "chain_60k.json")) as fh:
+        g = json.load(fh)
+    full = gen_contig(g["n"], g["seed"]).tobytes().decode()
+    seq = full[g["flank"]:len(full) - g["flank"]]
+    rows = np.zeros((len(g["rows"]), 8), np.int32)
+    rows[:, :4] = np.array(g["rows"], np.int32)
+    raw = finders.strict_records(np.frombuffer(seq.encode(), np.uint8), rows, g["chrom"], 0)
+    f = TandemRepeatFinder("/dev/null")
+    f.sequences, f.full_sequences, f.trim_offsets = {g["chrom"]: seq}, {g["chrom"]: full}, {g["chrom"]: g["flank"]}
+    kept = f._suppress_nested_short_calls(raw, overlap_threshold=0.5)
+    unique = f._deduplicate_repeats(kept)
+    merged = f._merge_adjacent_repeats(unique)
+    refined = f._refine_repeats(merged)
+    f._restore_reference_coordinates(refined)
+    refined = f._collapse_overlapping_repeats(refined)
+    final = [r for r in refined if r.copies >= f.min_copies and r.length >= 6]
+    final.sort(key=f._repeat_sort_key)
+    assert [len(raw), len(kept), len(unique), len(merged), len(refined), len(final)] == g["stage_counts"]
+    digest = lambda recs: hashlib.sha256("\n".join(repr(dataclasses.astuple(r)) for r in recs).encode()).hexdigest()
+    assert [r.to_bed() for r in final] == g["bed"]
+    assert digest(refined) == g["digest_before_filter"]
+    assert digest(final) == g["digest"]
+    # and the packaged entry point gives the same final list
+    again, dups = f._postprocess(finders.strict_records(np.frombuffer(seq.encode(), np.uint8), rows, g["chrom"], 0),
+                                 lambda msg: None)
+    assert digest(again) == g["digest"] and dups == g["stage_counts"][0] - g["stage_counts"][2]
