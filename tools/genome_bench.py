@@ -139,6 +139,14 @@ def main():
                "tier1_rows": int(sum(float(s[4]) for s in allst)), "strict_rows": int(sum(float(s[5]) for s in allst)),
                "per_rank_bases": [int(float(s[6])) for s in allst], "per_rank_s": [round(float(s[0]), 3) for s in allst],
                "rank0_contigs": per}
+        # honest end-to-end figure against the aggregate HBM roofline: compulsory bytes only (SURVEY 8d:
+        # index 20.2 B/base; Tier 1 and the strict scan read the text once each, 1 B/base + rows)
+        from bench import measured_peak
+        peak, src = measured_peak()
+        per_base = 20.2 + (0.0 if args.no_scans else 2.0)
+        out["compulsory_bytes_per_base"] = per_base
+        out["compulsory_fraction_of_aggregate_hbm"] = round(per_base * total / wall / 1e9 / (peak * world), 5)
+        out["hbm_peak_gbs_per_gpu"] = [peak, src]
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
