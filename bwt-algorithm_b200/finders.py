@@ -7,6 +7,7 @@ turned into ``TandemRepeat`` records here with the reference's float formulas.
 """
 from __future__ import annotations
 
+import gc
 from typing import Dict, List, Optional, Set, Tuple
 
 import numpy as np
@@ -69,23 +70,29 @@ def strict_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str, max_
     per_motif = {}
     pm = (1.0 - 0.0) * 100.0
     mm_per_copy = 0 if pm >= 99.9 else max_mismatch
-    for start, end, prim, count in rows[:, :4].tolist():
-        raw = text[start:start + prim]
-        known = per_motif.get(raw)
-        if known is None:
-            motif = raw.decode("ascii", errors="replace")
-            known = per_motif[raw] = (motif, MotifUtils.calculate_composition(motif),
-                                      MotifUtils.calculate_entropy(motif))
-        motif, comp, ent = known
-        length = end - start
-        actual = text[start:end].decode("ascii", errors="replace") if end <= size else motif * int(count)
-        score = max(0, int((length * (1.0 - 0.0) * 2) - (length * 0.0 * 7)))
-        out.append(TandemRepeat(
-            chrom=chromosome, start=start, end=end, motif=motif, copies=float(count), length=length,
-            tier=2, confidence=0.95, consensus_motif=motif, mismatch_rate=0.0,
-            max_mismatches_per_copy=mm_per_copy, n_copies_evaluated=count, strand="+",
-            percent_matches=pm, percent_indels=0.0, score=score, composition=dict(comp), entropy=ent,
-            actual_sequence=actual, variations=None))
+    append = out.append
+    # millions of records, each owning a dict: the cyclic collector would rescan the growing list
+    # again and again (it more than doubles the loop's time), and nothing here can form a cycle
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        for start, end, prim, count in rows[:, :4].tolist():
+            raw = text[start:start + prim]
+            known = per_motif.get(raw)
+            if known is None:
+                motif = raw.decode("ascii", errors="replace")
+                known = per_motif[raw] = (motif, MotifUtils.calculate_composition(motif),
+                                          MotifUtils.calculate_entropy(motif))
+            motif, comp, ent = known
+            length = end - start
+            actual = text[start:end].decode("ascii", errors="replace") if end <= size else motif * int(count)
+            score = max(0, int((length * (1.0 - 0.0) * 2) - (length * 0.0 * 7)))
+            # positional, in the field order of records.TandemRepeat (bwt.py:429-452)
+            append(TandemRepeat(chromosome, start, end, motif, float(count), length, 2, 0.95, motif, 0.0,
+                                mm_per_copy, count, "+", pm, 0.0, score, dict(comp), ent, actual, None))
+    finally:
+        if gc_was_on:
+            gc.enable()
     return out
 
 
