@@ -266,23 +266,29 @@ class MotifUtils:
         template = motif_template
         pos = start
         stop = min(total, max(end, start + k * min_copies) + max(k * 3, max_indel * 4))
+        fast = MotifUtils._EXACT_COPY_FAST_PATH
         while pos < stop:
+            if fast and sequence.startswith(template, pos):
+                # Exact copies: the banded DP would return the all-diagonal alignment (cost 0 at
+                # column k, every shorter end column costs >= 1, ties prefer the diagonal), and
+                # adding the template's own bases keeps every column's first-maximum tally, so
+                # the consensus does not move.  A run of exact copies is therefore taken in one
+                # step; most copies of a merged block are exact, which makes this the difference
+                # between O(k^2) and a string compare per copy.
+                run, nxt = 1, pos + k
+                while nxt < stop and sequence.startswith(template, nxt):
+                    run += 1
+                    nxt += k
+                units.extend([template] * run)
+                unit_ops.extend([] for _ in range(run))
+                errors.extend([0] * run)
+                for col, base in enumerate(template):
+                    tallies[col][base] += run
+                pos = nxt
+                continue
             window = sequence[pos:min(total, pos + k + max_indel)]
             if len(window) < k - max_indel:
                 break
-            if MotifUtils._EXACT_COPY_FAST_PATH and window.startswith(template):
-                # Exact copy: the banded DP would return the all-diagonal alignment (cost 0 at
-                # column k, every shorter end column costs >= 1, ties prefer the diagonal), and
-                # adding the template's own bases keeps every column's first-maximum tally, so
-                # the consensus does not move.  Most copies of a merged block are exact, which
-                # makes this the difference between O(k^2) and O(k) per copy.
-                units.append(template)
-                unit_ops.append([])
-                errors.append(0)
-                for col, base in enumerate(template):
-                    tallies[col][base] += 1
-                pos += k
-                continue
             res = MotifUtils._align_unit_to_window(template, window, max_indel, tol)
             if res is None or res.consumed == 0:
                 break
