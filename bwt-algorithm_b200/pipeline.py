@@ -244,9 +244,15 @@ class TandemRepeatFinder:
                 nested = False
                 first = int(r.start) >> 8
                 last = int(max(r.end - 1, r.start)) >> 8
+                # calls without mismatches come first, longest motif first: until the first call with
+                # mismatches every bucket list is non-increasing in motif length, and the first
+                # entry that is not longer than this call's motif ends the candidates
+                in_order = not (r.mismatch_rate > 0)
                 for b in range(first, last + 1):
                     for o_start, o_end, o_k in buckets.get(b, ()):
                         if o_k <= k:
+                            if in_order:
+                                break
                             continue
                         ov = max(0, min(r.end, o_end) - max(r.start, o_start))
                         if ov == 0:
