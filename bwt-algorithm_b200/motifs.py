@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import functools
 import math
+import operator
 from collections import Counter
 from typing import Dict, Iterator, List, Optional, Tuple
 
@@ -20,6 +21,7 @@ import numpy as np
 from .records import AlignmentResult, RepeatAlignmentSummary
 
 _COMPLEMENT = {"A": "T", "T": "A", "C": "G", "G": "C", "N": "N"}
+_COUNT_OF = operator.itemgetter(1)
 _TRANSITIONS = {("A", "G"), ("G", "A"), ("C", "T"), ("T", "C")}
 
 
@@ -236,7 +238,9 @@ class MotifUtils:
         out = []
         for idx, tally in enumerate(counts):
             if tally:
-                out.append(tally.most_common(1)[0][0])
+                # == tally.most_common(1)[0][0] (heapq.nlargest(1) is max(): the first maximum in
+                # insertion order), without the detour through heapq
+                out.append(max(tally.items(), key=_COUNT_OF)[0])
             else:
                 out.append(fallback[idx] if idx < len(fallback) else "N")
         return "".join(out)
