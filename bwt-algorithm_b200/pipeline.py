@@ -75,6 +75,40 @@ def _process_chromosome_worker(args):
         return []
 
 
+def _distinct_sort_names(names) -> bool:
+    keys = [_natural_sort_key(n) for n in names]
+    return len(set(keys)) == len(keys)
+
+
+def _finish_contig(chrom: str, seq: str, config: dict, left: str, right: str, raw: List["TandemRepeat"]):
+    """The post-processing chain of one contig, away from the parent: a finder that knows just this
+    contig (trimmed sequence for the re-alignments, flanks for the coordinate restore)."""
+    finder = TandemRepeatFinder(
+        "", sa_sample_rate=config["sa_sample_rate"], show_progress=config.get("show_progress", False),
+        allow_mismatches=config["allow_mismatches"], max_motif_length=config["max_motif_length"],
+        min_period=config["min_period"], max_period=config["max_period"], min_copies=config["min_copies"],
+        min_entropy=config["min_entropy"], flank_trim=len(left), max_unit_len=config["max_unit_len"])
+    finder.sequences = {chrom: seq}
+    finder.full_sequences = {chrom: left + seq + right}
+    finder.trim_offsets = {chrom: len(left)}
+    return finder._postprocess_counts(raw)
+
+
+def _process_and_finish_contig(args):
+    """Worker of the multi-process path: detection (bwt.py:3040-3141), then this contig's share of the
+    post-processing chain.  Returns (final calls, raw, after suppression, after dedup)."""
+    chrom, seq, config, left, right = args
+    raw = _process_chromosome_worker((chrom, seq, config))
+    try:
+        return _finish_contig(chrom, seq, config, left, right, raw)
+    except Exception as exc:  # same policy as the detection worker
+        print(f"ERROR post-processing chromosome {chrom}: {exc}")
+        import traceback
+
+        traceback.print_exc()
+        return [], len(raw), len(raw), len(raw)
+
+
 class TandemRepeatFinder:
     """Coordinates loading, detection, post-processing and output (bwt.py:3144-4198)."""
 
@@ -156,10 +190,10 @@ class TandemRepeatFinder:
             "max_unit_len": self.max_unit_len,
         }
 
-    def _postprocess(self, raw: List[TandemRepeat], announce) -> Tuple[List[TandemRepeat], int]:
+    def _postprocess_counts(self, raw: List[TandemRepeat]) -> Tuple[List[TandemRepeat], int, int, int]:
+        """The chain of bwt.py:3827-3846 / 3928-3952; returns the final calls and the sizes of the raw,
+        nested-call-suppressed and deduplicated lists."""
         kept = self._suppress_nested_short_calls(raw, overlap_threshold=0.5)
-        if len(kept) < len(raw):
-            announce(f"Nested call suppression: {len(raw)} -> {len(kept)} repeats")
         unique = self._deduplicate_repeats(kept)
         merged = self._merge_adjacent_repeats(unique)
         refined = self._refine_repeats(merged)
@@ -167,7 +201,13 @@ class TandemRepeatFinder:
         refined = self._collapse_overlapping_repeats(refined)
         final = [r for r in refined if r.copies >= self.min_copies and r.length >= 6]
         final.sort(key=self._repeat_sort_key)
-        return final, len(raw) - len(unique)
+        return final, len(raw), len(kept), len(unique)
+
+    def _postprocess(self, raw: List[TandemRepeat], announce) -> Tuple[List[TandemRepeat], int]:
+        final, n_raw, n_kept, n_unique = self._postprocess_counts(raw)
+        if n_kept < n_raw:
+            announce(f"Nested call suppression: {n_raw} -> {n_kept} repeats")
+        return final, n_raw - n_unique
 
     def find_tandem_repeats(self, enable_tier1: bool = True, enable_tier2: bool = True, enable_tier3: bool = False,
                             long_reads: Optional[List[str]] = None) -> List[TandemRepeat]:
@@ -206,20 +246,52 @@ class TandemRepeatFinder:
         t0 = time.time()
         raw: List[TandemRepeat] = []
         done = 0
-        for got in sharding.run_tasks(_process_chromosome_worker, tasks, n_jobs):
-            raw.extend(got)
-            done += 1
-            print(f"\r[{_bar(done, len(tasks))}] {done / len(tasks) * 100:.1f}% ({done}/{len(tasks)}) "
-                  f"chromosomes completed - {_elapsed(t0)}", end="", flush=True)
-        print()
-        if enable_tier3 and long_reads:
-            raise NotImplementedError("Tier 3 (long reads) is outside the B200 hot path")
-        final, dup = self._postprocess(raw, lambda m: print("\n" + m))
+        # Every stage of the post-processing chain works inside one contig (calls of different contigs
+        # never nest, merge or collapse), so when the contigs go to several worker processes each worker
+        # finishes its contigs itself: the chain runs in parallel and only the final calls (a few percent
+        # of the raw ones) are pickled back.  Needs contig names with distinct sort keys, so that sorting
+        # the concatenation equals the chain's own sorts of the mixed list.
+        per_contig = (sharding.worker_processes(len(tasks), n_jobs) > 1
+                      and _distinct_sort_names(self.sequences) and not (enable_tier3 and long_reads))
+        if per_contig:
+            finished: List[TandemRepeat] = []
+            n_raw = n_kept = n_unique = 0
+            for part, a, b, c in sharding.run_tasks(_process_and_finish_contig, self._finish_tasks(tasks), n_jobs):
+                finished.extend(part)
+                n_raw, n_kept, n_unique = n_raw + a, n_kept + b, n_unique + c
+                done += 1
+                print(f"\r[{_bar(done, len(tasks))}] {done / len(tasks) * 100:.1f}% ({done}/{len(tasks)}) "
+                      f"chromosomes completed - {_elapsed(t0)}", end="", flush=True)
+            print()
+            if n_kept < n_raw:
+                print("\n" + f"Nested call suppression: {n_raw} -> {n_kept} repeats")
+            finished.sort(key=self._repeat_sort_key)
+            final, dup = finished, n_raw - n_unique
+        else:
+            for got in sharding.run_tasks(_process_chromosome_worker, tasks, n_jobs):
+                raw.extend(got)
+                done += 1
+                print(f"\r[{_bar(done, len(tasks))}] {done / len(tasks) * 100:.1f}% ({done}/{len(tasks)}) "
+                      f"chromosomes completed - {_elapsed(t0)}", end="", flush=True)
+            print()
+            if enable_tier3 and long_reads:
+                raise NotImplementedError("Tier 3 (long reads) is outside the B200 hot path")
+            final, dup = self._postprocess(raw, lambda m: print("\n" + m))
         if dup > 0:
             print(f"Analysis complete! Found {len(final)} unique repeats (deduplicated {dup}).")
         else:
             print(f"Analysis complete! Found {len(final)} unique repeats.")
         return final
+
+    def _finish_tasks(self, tasks: List[Tuple]) -> List[Tuple]:
+        """(chrom, seq, config) -> (chrom, seq, config, left flank, right flank): what a worker needs to
+        restore reference coordinates (bwt.py:3499-3513) without the parent's dictionaries."""
+        out = []
+        for chrom, seq, cfg in tasks:
+            full = self.full_sequences.get(chrom) or ""
+            left = self.trim_offsets.get(chrom, 0)
+            out.append((chrom, seq, cfg, full[:left], full[left + len(seq):]))
+        return out
 
     # ------------------------------------------------------------------ post-processing
     def _suppress_nested_short_calls(self, repeats: List[TandemRepeat],

@@ -51,10 +51,15 @@ def _run_bin(args):
     return [worker(t) for t in tasks]
 
 
+def worker_processes(n_tasks: int, n_jobs: int) -> int:
+    """How many worker processes ``run_tasks`` uses for `n_tasks` contigs (1 = in-process)."""
+    return max(1, min(_gpu_count(), int(n_tasks), max(1, int(n_jobs or 1))))
+
+
 def run_tasks(worker: Callable, tasks: List[Tuple], n_jobs: int) -> Iterator[list]:
     """Yields worker(task) results (any order).  One process per GPU when several
     GPUs are visible and there are several contigs; otherwise in-process."""
-    ngpu = min(_gpu_count(), len(tasks), max(1, int(n_jobs or 1)))
+    ngpu = worker_processes(len(tasks), n_jobs)
     if ngpu <= 1:
         for t in tasks:
             yield worker(t)

@@ -225,3 +225,47 @@ def test_postprocessing_chain_equals_reference_golden():
     again, dups = f._postprocess(finders.strict_records(np.frombuffer(seq.encode(), np.uint8), rows, g["chrom"], 0),
                                  lambda msg: None)
     assert digest(again) == g["digest"] and dups == g["stage_counts"][0] - g["stage_counts"][2]
+
+
+def test_per_contig_finish_equals_global_chain(oracle, tmp_path):
+    """The multi-process path lets every worker run the chain on its own contigs
+    (pipeline._finish_contig) and sorts the concatenation; same calls, same counts as the chain on the
+    mixed list, on the reference's 12-contig fixture and on planted contigs with flank trimming."""
+    import dataclasses
+    import os
+    import pickle
+
+    from bwt_algorithm_b200 import pipeline
+    from tests.util import gen_contig
+
+    planted = tmp_path / "planted.fa"
+    with open(planted, "w") as fh:
+        for i, n in enumerate((12_000, 5_000, 50, 8_000)):
+            fh.write(f">ctg{10 - i} planted\n{gen_contig(n, 40 + i).tobytes().decode()}\n")
+    fixture = os.path.join(os.path.dirname(__file__), "golden", "cli", "test2.fa")
+    for path, trim in ((fixture, 30), (str(planted), 30), (str(planted), 0)):
+        finder = TandemRepeatFinder(path, flank_trim=trim)
+        seqs = finder.load_reference()
+        assert len(seqs) >= 4 and pipeline._distinct_sort_names(seqs)
+        cfg = finder._config(True, True)
+        raw_of = {}
+        for chrom, seq in seqs.items():
+            text = (seq + "$").encode()
+            rows = oracle.strict_scan(text, 1, max(120, min(len(seq) // 3, 1000)), 0, 3)
+            raw_of[chrom] = lambda text=text, rows=rows, chrom=chrom: finders.strict_records(
+                np.frombuffer(text, np.uint8), rows, chrom, 0)
+        mixed = [r for chrom in seqs for r in raw_of[chrom]()]
+        want, n_raw, n_kept, n_unique = finder._postprocess_counts(mixed)
+        got, sums = [], [0, 0, 0]
+        tasks = finder._finish_tasks([(chrom, seq, cfg) for chrom, seq in seqs.items()])
+        for chrom, seq, c, left, right in reversed(tasks):          # workers finish in any order
+            assert left + seq + right == finder.full_sequences[chrom] and len(left) == finder.trim_offsets[chrom]
+            part, a, b, c3 = pipeline._finish_contig(chrom, seq, c, left, right, raw_of[chrom]())
+            got.extend(part)
+            sums = [sums[0] + a, sums[1] + b, sums[2] + c3]
+        got.sort(key=finder._repeat_sort_key)
+        assert sums == [n_raw, n_kept, n_unique]
+        assert [dataclasses.astuple(r) for r in got] == [dataclasses.astuple(r) for r in want]
+        assert len(want) > 0
+    pickle.dumps(pipeline._process_and_finish_contig)                # spawn-able: top level, importable
+    assert not pipeline._distinct_sort_names(["chr1", "Chr1"])       # equal sort keys: the global chain is used
