@@ -269,3 +269,33 @@ def test_per_contig_finish_equals_global_chain(oracle, tmp_path):
         assert len(want) > 0
     pickle.dumps(pipeline._process_and_finish_contig)                # spawn-able: top level, importable
     assert not pipeline._distinct_sort_names(["chr1", "Chr1"])       # equal sort keys: the global chain is used
+
+
+def test_parallel_driver_per_contig_branch(oracle, monkeypatch, capsys):
+    """find_tandem_repeats_parallel with several worker processes (simulated in-process, detection
+    served by the oracle) returns what the single-process branch returns, with the same summary lines."""
+    import dataclasses
+    import os
+
+    from bwt_algorithm_b200 import pipeline, sharding
+
+    def fake_detection(args):
+        chrom, seq, config = args
+        text = (seq + "$").encode()
+        rows = oracle.strict_scan(text, 1, max(config["max_unit_len"], min(len(seq) // config["min_copies"], 1000)),
+                                  0, config["min_copies"])
+        return finders.strict_records(np.frombuffer(text, np.uint8), rows, chrom, 0)
+
+    monkeypatch.setattr(pipeline, "_process_chromosome_worker", fake_detection)
+    fixture = os.path.join(os.path.dirname(__file__), "golden", "cli", "test2.fa")
+    outs = []
+    for procs in (1, 2):
+        monkeypatch.setattr(sharding, "worker_processes", lambda n_tasks, n_jobs, procs=procs: procs)
+        monkeypatch.setattr(sharding, "run_tasks", lambda worker, tasks, n_jobs: (worker(t) for t in tasks))
+        finder = TandemRepeatFinder(fixture)
+        finder.load_reference()
+        final = finder.find_tandem_repeats_parallel(enable_tier1=False, enable_tier2=True, n_jobs=4)
+        text = capsys.readouterr().out
+        outs.append(([dataclasses.astuple(r) for r in final],
+                     [ln for ln in text.splitlines() if ln.startswith(("Nested call", "Analysis complete"))]))
+    assert outs[0] == outs[1] and len(outs[0][0]) > 0 and len(outs[0][1]) == 2
