@@ -320,14 +320,16 @@ class TandemRepeatFinder:
                 # mismatches every bucket list is non-increasing in motif length, and the first
                 # entry that is not longer than this call's motif ends the candidates
                 in_order = not (r.mismatch_rate > 0)
+                r_start, r_end = r.start, r.end
                 for b in range(first, last + 1):
                     for o_start, o_end, o_k in buckets.get(b, ()):
                         if o_k <= k:
                             if in_order:
                                 break
                             continue
-                        ov = max(0, min(r.end, o_end) - max(r.start, o_start))
-                        if ov == 0:
+                        # ov = max(0, min(r.end, o_end) - max(r.start, o_start)), spelled without calls
+                        ov = (r_end if r_end < o_end else o_end) - (r_start if r_start > o_start else o_start)
+                        if ov <= 0:
                             continue
                         if k == 1 and o_k > 1 and ov / span >= 0.8:
                             nested = True
