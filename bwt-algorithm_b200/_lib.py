@@ -61,6 +61,12 @@ _SIGS = {
     "bwtk_bsearch_batch": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p]),
     "bwtk_bsearch_motif_sweep": (_i32, [_p, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _p, _p, _p]),
     "bwtk_rank_batch": (_i32, [_p, _p, _i64, _i32, _p, _i64, _p, _p, _i64, _p, _p]),
+    "bwtk_fm_pack_bytes": (_i64, [_i64]),
+    "bwtk_fm_pack_workspace_bytes": (_i64, [_i64, _i64]),
+    "bwtk_fm_pack": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p]),
+    "bwtk_fm_search_batch": (_i32, [_p, _p, _i64, _p, _i64, _p, _p, _i32, _p]),
+    "bwtk_fm_rank_batch": (_i32, [_p, _p, _p, _i64, _p, _p]),
+    "bwtk_fm_motif_sweep": (_i32, [_p, _i32, _p, _p, _i32, _p]),
     "bwtk_tier1_workspace_bytes": (_i64, [_i64]),
     "bwtk_tier1_scan": (_i32, [_p, _i64, _i32, _i32, _i32, C.c_double, _p, _i64, _p, _p, _p, _i64, _p]),
     "bwtk_strict_workspace_bytes": (_i64, [_i64, _i64]),
@@ -74,6 +80,15 @@ _SIGS = {
 }
 
 EXPORTS = tuple(_SIGS.keys())
+
+FM_L2_PERSIST = 1
+
+
+class FmIndex(C.Structure):
+    """``bwtk_fm_index`` of include/bwtk.h (device pointers as integers)."""
+    _fields_ = [("d_blocks", _p), ("n", _i64), ("d_exc_pos", _p), ("d_exc_by_code", _p), ("n_exc", _i64),
+                ("d_code_off", _p), ("d_C", _p), ("d_tot", _p), ("acgt_C", _i64 * 4), ("acgt_tot", _i64 * 4),
+                ("d_ftab_sp", _p), ("d_ftab_ep", _p), ("ftab_k", _i32)]
 
 
 def lib():

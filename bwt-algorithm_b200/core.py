@@ -234,7 +234,7 @@ class BWTCore:
 
     def rank(self, char: Union[str, int], pos: int) -> int:
         """# of `char` in bwt[0:pos] (bwt.py:335-357)."""
-        if pos <= 0:
+        if pos <= 0 or self.n == 0:
             return 0
         code = ord(char) if isinstance(char, str) else int(char)
         if code < 0 or code > 255:
@@ -245,14 +245,18 @@ class BWTCore:
         """Inclusive SA interval of `pattern`, (-1,-1) if absent (bwt.py:359-389)."""
         if not pattern:
             return (0, self.n - 1)
-        if any(ord(c) > 255 for c in pattern):
+        if self.n == 0 or any(ord(c) > 255 for c in pattern):
             return (-1, -1)
         sp, ep = self.device_index.backward_search_batch([pattern.encode("latin1")])
         return (int(sp[0]), int(ep[0]))
 
     def backward_search_many(self, patterns) -> Tuple[np.ndarray, np.ndarray]:
         """Batched form of ``backward_search`` (one kernel launch)."""
-        return self.device_index.backward_search_batch(list(patterns))
+        patterns = list(patterns)
+        if self.n == 0:      # empty text: every non-empty pattern is absent (bwt.py:371-389)
+            sp = np.array([0 if not p else -1 for p in patterns], np.int32)
+            return sp, np.where(sp == 0, self.n - 1, -1).astype(np.int32)
+        return self.device_index.backward_search_batch(patterns)
 
     def count_occurrences(self, pattern: str) -> int:
         sp, ep = self.backward_search(pattern)

@@ -28,17 +28,82 @@ class _FMSearch:
     """Rank / backward search over (bwt, occ, C) held on one device; shared by the full
     ``DeviceIndex`` and the search-only ``FMReplica``."""
 
+    # ------------------------------------------------------------------ packed search index
+    #: searches run over the 64-byte rank blocks (bwtk_fm_*); False = the byte BWT + Occ rows
+    use_packed = True
+    #: length of the k-mer interval table that seeds longer patterns (0 = none)
+    ftab_k = 0
+    #: keep the rank blocks resident in L2 while a batch streams through
+    l2_persist = True
+
+    def ensure_packed(self):
+        """Builds the packed search index (bwtk_fm_pack) from the BWT bytes on first use."""
+        if getattr(self, "_fm", None) is not None:
+            return self._fm
+        torch, L, n = self.torch, _lib.lib(), self.n
+        if n < 1:
+            raise _lib.BwtkError("empty text has no search index")
+        tot = np.ascontiguousarray(self.totals, np.int64)
+        n_exc = int(n - sum(int(tot[c]) for c in b"ACGT"))
+        with torch.cuda.device(self.device):
+            blocks = torch.empty(int(L.bwtk_fm_pack_bytes(n)), dtype=torch.uint8, device=self.device)
+            exc_pos = torch.empty(max(n_exc, 1), dtype=torch.int32, device=self.device)
+            exc_by_code = torch.empty(max(n_exc, 1), dtype=torch.int32, device=self.device)
+            code_off = torch.zeros(257, dtype=torch.int64, device=self.device)
+            wsb = int(L.bwtk_fm_pack_workspace_bytes(n, n_exc))
+            ws = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+            cnt = C.c_int64(0)
+            _lib.check(L.bwtk_fm_pack(self.bwt.data_ptr(), n, tot.ctypes.data, blocks.data_ptr(), exc_pos.data_ptr(),
+                                      exc_by_code.data_ptr(), max(n_exc, 1), code_off.data_ptr(), C.addressof(cnt),
+                                      ws.data_ptr(), wsb, _lib.stream_ptr()), "fm_pack")
+        fx = _lib.FmIndex()
+        fx.d_blocks, fx.n = blocks.data_ptr(), n
+        fx.d_exc_pos, fx.d_exc_by_code, fx.n_exc = exc_pos.data_ptr(), exc_by_code.data_ptr(), int(cnt.value)
+        fx.d_code_off, fx.d_C, fx.d_tot = code_off.data_ptr(), self.d_C.data_ptr(), self.d_tot.data_ptr()
+        counts = np.concatenate(([0], np.cumsum(tot)[:-1]))
+        for k, c in enumerate(b"ACGT"):
+            fx.acgt_C[k] = int(counts[c])
+            fx.acgt_tot[k] = int(tot[c])
+        fx.d_ftab_sp = fx.d_ftab_ep = None
+        fx.ftab_k = 0
+        self._fm = fx
+        self._fm_keep = (blocks, exc_pos, exc_by_code, code_off)      # the struct holds raw pointers
+        self.packed_bytes = blocks.numel() + 8 * int(cnt.value)
+        if self.ftab_k:
+            self.build_ftab(self.ftab_k)
+        return fx
+
+    def build_ftab(self, k: int):
+        """Interval table of every ACGT k-mer (level k of the motif sweep): patterns of length >= k
+        whose last k characters are ACGT start from it and do k fewer LF steps."""
+        fx = self.ensure_packed() if getattr(self, "_fm", None) is None else self._fm
+        fx.ftab_k = 0
+        sp, ep = self.motif_sweep(k)
+        off = (4 ** k - 4) // 3
+        self._ftab = (sp[off:off + 4 ** k].contiguous(), ep[off:off + 4 ** k].contiguous())
+        fx.d_ftab_sp, fx.d_ftab_ep, fx.ftab_k = self._ftab[0].data_ptr(), self._ftab[1].data_ptr(), int(k)
+        self.ftab_k = int(k)
+
+    def _flags(self) -> int:
+        return _lib.FM_L2_PERSIST if self.l2_persist else 0
+
     # ------------------------------------------------------------------ a8 / a9
     def search_device(self, d_pats, stride: int, d_lens, nq: int):
         torch, L = self.torch, _lib.lib()
         with torch.cuda.device(self.device):
             sp = torch.empty(nq, dtype=torch.int32, device=self.device)
             ep = torch.empty(nq, dtype=torch.int32, device=self.device)
-            _lib.check(L.bwtk_bsearch_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
-                                            self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
-                                            self.d_row.data_ptr(), self.n, _lib.ptr(d_pats), stride,
-                                            d_lens.data_ptr(), nq, sp.data_ptr(), ep.data_ptr(),
-                                            _lib.stream_ptr()), "bsearch_batch")
+            if self.use_packed and self.n >= 1:
+                fx = self.ensure_packed()
+                _lib.check(L.bwtk_fm_search_batch(C.addressof(fx), _lib.ptr(d_pats), stride, d_lens.data_ptr(), nq,
+                                                  sp.data_ptr(), ep.data_ptr(), self._flags(), _lib.stream_ptr()),
+                           "fm_search_batch")
+            else:
+                _lib.check(L.bwtk_bsearch_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
+                                                self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
+                                                self.d_row.data_ptr(), self.n, _lib.ptr(d_pats), stride,
+                                                d_lens.data_ptr(), nq, sp.data_ptr(), ep.data_ptr(),
+                                                _lib.stream_ptr()), "bsearch_batch")
         return sp, ep
 
     def search_block(self, d_pats, d_lens):
@@ -76,6 +141,11 @@ class _FMSearch:
         with torch.cuda.device(self.device):
             sp = torch.empty(total, dtype=torch.int32, device=self.device)
             ep = torch.empty(total, dtype=torch.int32, device=self.device)
+            if self.use_packed and self.n >= 1:
+                fx = self.ensure_packed()
+                _lib.check(L.bwtk_fm_motif_sweep(C.addressof(fx), kmax, sp.data_ptr(), ep.data_ptr(), self._flags(),
+                                                 _lib.stream_ptr()), "fm_motif_sweep")
+                return sp, ep
             _lib.check(L.bwtk_bsearch_motif_sweep(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
                                                   self.occ_rate, self.d_C.data_ptr(), self.d_tot.data_ptr(),
                                                   self.d_row.data_ptr(), self.n, kmax, sp.data_ptr(),
@@ -91,6 +161,11 @@ class _FMSearch:
             d_c = torch.tensor(list(codes), dtype=torch.int32, device=self.device)
             d_p = torch.tensor(list(positions), dtype=torch.int64, device=self.device)
             out = torch.empty(nq, dtype=torch.int64, device=self.device)
+            if self.use_packed and self.n >= 1:
+                fx = self.ensure_packed()
+                _lib.check(L.bwtk_fm_rank_batch(C.addressof(fx), d_c.data_ptr(), d_p.data_ptr(), nq, out.data_ptr(),
+                                                _lib.stream_ptr()), "fm_rank_batch")
+                return out.cpu().numpy()
             _lib.check(L.bwtk_rank_batch(self.bwt.data_ptr(), self.occ.data_ptr(), self.occ.shape[1],
                                          self.occ_rate, self.d_row.data_ptr(), self.n, d_c.data_ptr(),
                                          d_p.data_ptr(), nq, out.data_ptr(), _lib.stream_ptr()), "rank_batch")
@@ -208,7 +283,14 @@ class DeviceIndex(_FMSearch):
         self._lcp = up(host["lcp"]) if "lcp" in host else None
         self.sa_stats = np.zeros(8, np.int64)
         self.ncp = (n // self.occ_rate + 1 + (1 if n % self.occ_rate else 0)) if n else 0
-        self._set_alphabet(host["totals"].astype(np.int64), host["row"].astype(np.int32))
+        row = host["row"].astype(np.int32)
+        nrows = int((row >= 0).sum())
+        if n and (self.occ.dtype != torch.int32 or tuple(self.occ.shape) != (nrows, self.ncp)
+                  or self.bwt.dtype != torch.uint8 or self.text.dtype != torch.uint8
+                  or int(host["totals"].astype(np.int64).sum()) != n):
+            raise ValueError(f"{path}: Occ table {tuple(self.occ.shape)}/{self.occ.dtype} does not match "
+                             f"({nrows}, {self.ncp}) int32 for n={n}, occ_rate={self.occ_rate}")
+        self._set_alphabet(host["totals"].astype(np.int64), row)
         self.kmer_off = self.kmer_pos = None
         self.kmer_count = 0
         if build_kmer:

@@ -109,6 +109,32 @@ def _process_and_finish_contig(args):
         return [], len(raw), len(raw), len(raw)
 
 
+class _LazyCores(dict):
+    """``bwt_cores`` of the CLI path: chrom -> BWTCore, each built on first access."""
+
+    def __init__(self, sequences: Dict[str, str], sa_sample_rate: int):
+        super().__init__()
+        self._sequences = sequences
+        self._rate = sa_sample_rate
+
+    def __missing__(self, chrom):
+        core = BWTCore(self._sequences[chrom] + "$", self._rate)
+        self[chrom] = core
+        return core
+
+    def items(self):
+        return ((c, self[c]) for c in self._sequences)
+
+    def __iter__(self):
+        return iter(self._sequences)
+
+    def __len__(self):
+        return len(self._sequences)
+
+    def __contains__(self, chrom):
+        return chrom in self._sequences
+
+
 class TandemRepeatFinder:
     """Coordinates loading, detection, post-processing and output (bwt.py:3144-4198)."""
 
@@ -167,16 +193,22 @@ class TandemRepeatFinder:
         self.sequences = sequences
         return sequences
 
-    def build_indices(self, sequences: Dict[str, str]):
-        """One BWTCore per contig, kept in self.bwt_cores (bwt.py:3758-3790)."""
+    def build_indices(self, sequences: Dict[str, str], lazy: bool = False):
+        """One BWTCore per contig in self.bwt_cores (bwt.py:3758-3790).  With ``lazy`` (the CLI path) a
+        contig's index is built when ``bwt_cores[chrom]`` is first read: the per-contig workers build
+        their own index on their own GPU, so building every contig here as well would double the build
+        time and hold ~10 B/base of HBM on GPU 0 for nothing."""
         items = list(sequences.items())
         print("Building BWT indices...")
         t0 = time.time()
+        if lazy:
+            self.bwt_cores = _LazyCores(sequences, self.sa_sample_rate)
         for idx, (chrom, seq) in enumerate(items, 1):
             pct = (idx - 1) / len(items) * 100
             print(f"\r[{_bar(idx - 1, len(items))}] {pct:.1f}% Building index for {chrom} ({len(seq):,} bp) - "
                   f"{_elapsed(t0)}", end="", flush=True)
-            self.bwt_cores[chrom] = BWTCore(seq + "$", self.sa_sample_rate)
+            if not lazy:
+                self.bwt_cores[chrom] = BWTCore(seq + "$", self.sa_sample_rate)
         print(f"\r[{'█' * _BAR}] 100.0% BWT indices built for {len(items)} chromosome(s) - {_elapsed(t0)}     ")
         print()
 
@@ -764,8 +796,17 @@ def main(argv=None):
                                 min_period=args.min_period, max_period=args.max_period, min_copies=args.min_copies,
                                 min_entropy=args.min_entropy, flank_trim=args.flank_trim,
                                 max_unit_len=args.max_unit_len)
+    if args.min_copies < 2:
+        # the strict adjacency scan counts runs of (min_copies - 1) matching unit shifts; the reference's
+        # one-copy "repeats" (every position, every unit length) are not supported -- say so instead of
+        # letting the worker's blanket except turn an argument error into an empty result
+        raise SystemExit("error: --min-copies must be at least 2 on the B200 path")
     sequences = finder.load_reference()
-    finder.build_indices(sequences)
+    too_long = [c for c, s in sequences.items() if len(s) + 1 >= (1 << 30)]
+    if too_long:
+        raise SystemExit(f"error: contig(s) {', '.join(too_long)} exceed 2^30 symbols "
+                         "(int32 suffix arrays, as in the reference)")
+    finder.build_indices(sequences, lazy=True)
     if args.long_reads and args.tier3:
         raise SystemExit("Tier 3 (long reads) is outside the B200 hot path and is not provided")
     if args.jobs != -1:

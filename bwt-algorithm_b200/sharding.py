@@ -106,6 +106,49 @@ def gather_rows(rows: np.ndarray, contig_ids: np.ndarray, group=None, device=Non
     return merged[:, :REC_W].copy(), merged[:, REC_W].copy()
 
 
+def gather_rows_to_rank0(rows, table: Sequence[Sequence[int]], group=None, out=None):
+    """Device-side form of ``gather_rows`` for a genome's worth of rows (the merge of the per-contig
+    results, bwt.py:3896-3899): every rank passes ONE tensor ``rows`` (int32[R, 8], on its GPU under
+    NCCL, on the CPU under gloo) and a small ``table`` of (contig id, kind, first row, count) entries
+    describing it.  Rank 0 receives the rows of all ranks back to back in one tensor on its own device
+    (written straight into ``out`` when given) plus the merged table with row offsets rebased; the
+    other ranks get (None, None).  Exact-size point-to-point transfers (over NVLink between GPUs), no
+    padding and no copy to ranks that do not need the rows: one all_gather of the counts, one object
+    gather of the tables, then one batched send/recv."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rows = rows.reshape(-1, REC_W)
+    dev = rows.device
+    count = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    tables = [None] * world
+    dist.all_gather_object(tables, [tuple(int(x) for x in e) for e in table], group=group)
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    if rank != 0:
+        if counts[rank]:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, rows.contiguous(), 0, group=group)]):
+                w.wait()
+        return None, None
+    total = int(starts[-1])
+    if out is None:
+        out = torch.empty((total, REC_W), dtype=torch.int32, device=dev)
+    elif out.shape[0] < total:
+        raise ValueError(f"gather_rows_to_rank0: out holds {out.shape[0]} rows, {total} needed")
+    out[: counts[0]].copy_(rows)
+    ops = [dist.P2POp(dist.irecv, out[int(starts[r]): int(starts[r + 1])], r, group=group)
+           for r in range(1, world) if counts[r]]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    merged = [(cid, kind, first + int(starts[r]), cnt) for r in range(world) for cid, kind, first, cnt in tables[r]]
+    return out[:total], merged
+
+
 # ---------------------------------------------------------------------------
 # one contig, many GPUs: the motif batch is split, the index is replicated
 # ---------------------------------------------------------------------------

@@ -125,9 +125,14 @@ class IndexPipeline:
         slot = self.slots[ticket % len(self.slots)]
         slot.done.synchronize()
         n = slot.n
+        ncp = n // self.occ_rate + 1 + (1 if n % self.occ_rate else 0)
+        nrows = int(slot.stats[7])
+        # bwtk_index_build writes Occ rows with stride ncp(n), not with the slot's capacity stride, and the
+        # slot's buffer is overwritten by the next submit: hand out a right-shaped copy (device tensor)
+        occ = slot.occ.view(-1)[: nrows * ncp].view(nrows, ncp).clone()
         out = {"n": n, "sa": slot.h_sa[:n].numpy(), "bwt": slot.h_bwt[:n].numpy(),
                "totals": slot.totals.copy(), "row_of_code": slot.row.copy(), "stats": slot.stats.copy(),
-               "occ": slot.occ, "ncp": n // self.occ_rate + 1 + (1 if n % self.occ_rate else 0)}
+               "occ": occ, "ncp": ncp}
         if slot.h_lcp is not None:
             out["lcp"] = slot.h_lcp[:n].numpy()
         return out

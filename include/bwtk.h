@@ -144,6 +144,54 @@ int32_t bwtk_rank_batch(const uint8_t *d_bwt, const int32_t *d_occ, int64_t ncp,
                         const int32_t *d_row_of_code, int64_t n, const int32_t *d_codes,
                         const int64_t *d_pos, int64_t nq, int64_t *d_out, void *stream);
 
+/* ---- a8/a9 on a packed index: rank / backward_search (bwt.py:335-389) ---------
+ * The search side of the FM index as 64-byte rank blocks: block b covers BWT
+ * positions [192 b, 192 b + 192) and holds #A, #C, #G, #T before the block
+ * (4 x u32) followed by the 192 symbols at 2 bits each, so one rank is one
+ * random access (counts + first 64 symbols in the first 32-B sector).  Bytes
+ * other than A/C/G/T are "exceptions": stored as code 0 and listed by position
+ * (d_exc_pos, ascending) and grouped by byte value (d_exc_by_code with group
+ * offsets d_code_off[257]).  Answers are identical to bwtk_bsearch_batch /
+ * bwtk_rank_batch / bwtk_bsearch_motif_sweep over the byte BWT + Occ rows.
+ *
+ * bwtk_fm_pack builds the arrays from the BWT bytes.  h_totals[256]: byte counts
+ * (as returned by bwtk_index_build); the number of exceptions is
+ * n - totals[A,C,G,T] and is written to *h_exc_count (BWTK_EOVERFLOW if it
+ * exceeds exc_cap).  d_blocks: bwtk_fm_pack_bytes(n) bytes, 16-byte aligned.
+ * Synchronises the stream. */
+typedef struct bwtk_fm_index {
+    const void *d_blocks;          /* bwtk_fm_pack_bytes(n) bytes */
+    int64_t n;                     /* BWT length */
+    const uint32_t *d_exc_pos;     /* [n_exc] */
+    const uint32_t *d_exc_by_code; /* [n_exc] */
+    int64_t n_exc;
+    const int64_t *d_code_off;     /* [257] */
+    const int64_t *d_C;            /* [256] C array */
+    const int64_t *d_tot;          /* [256] byte totals */
+    int64_t acgt_C[4];             /* host copies of C / totals of A, C, G, T */
+    int64_t acgt_tot[4];
+    const int32_t *d_ftab_sp;      /* optional: intervals of all 4^ftab_k ACGT k-mers, index = base-4 */
+    const int32_t *d_ftab_ep;      /*   value, first character most significant (a level of the motif sweep) */
+    int32_t ftab_k;                /* 0 = no table */
+} bwtk_fm_index;
+#define BWTK_FM_L2_PERSIST 1       /* flags: keep the rank blocks resident in L2 (access policy window) */
+int64_t bwtk_fm_pack_bytes(int64_t n);
+int64_t bwtk_fm_pack_workspace_bytes(int64_t n, int64_t n_exc);
+int32_t bwtk_fm_pack(const uint8_t *d_bwt, int64_t n, const int64_t *h_totals, void *d_blocks,
+                     uint32_t *d_exc_pos, uint32_t *d_exc_by_code, int64_t exc_cap, int64_t *d_code_off,
+                     int64_t *h_exc_count, void *d_ws, int64_t ws_bytes, void *stream);
+/* as bwtk_bsearch_batch; with a k-mer table, patterns of length >= ftab_k whose last ftab_k
+ * characters are ACGT start from that k-mer's interval (same answers, fewer LF steps) */
+int32_t bwtk_fm_search_batch(const bwtk_fm_index *ix, const uint8_t *d_pats, int64_t stride,
+                             const int32_t *d_lens, int64_t nq, int32_t *d_sp, int32_t *d_ep,
+                             int32_t flags, void *stream);
+/* as bwtk_rank_batch */
+int32_t bwtk_fm_rank_batch(const bwtk_fm_index *ix, const int32_t *d_codes, const int64_t *d_pos,
+                           int64_t nq, int64_t *d_out, void *stream);
+/* as bwtk_bsearch_motif_sweep: both blocks of a parent motif serve its four children */
+int32_t bwtk_fm_motif_sweep(const bwtk_fm_index *ix, int32_t kmax, int32_t *d_sp, int32_t *d_ep,
+                            int32_t flags, void *stream);
+
 /* ---- a12: Tier1STRFinder._find_simple_tandems_kmer (bwt.py:1426-1531) ---
  * rows: start,end,motif_len,copies,0,0,0,0 in the reference's emission order.
  * d_seen_out (may be NULL): n bytes, the final seen mask. */

@@ -78,7 +78,8 @@ sys.path.insert(0, {root!r})
 import numpy as np
 import torch.distributed as dist
 import bwt_algorithm_b200
-from bwt_algorithm_b200.sharding import gather_rows, lpt_partition
+import torch
+from bwt_algorithm_b200.sharding import gather_rows, gather_rows_to_rank0, lpt_partition
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 lens = [900, 500, 400, 300, 100]
@@ -100,9 +101,22 @@ if rank == 0:
     for c, L in enumerate(lens):
         sel = allrows[allids == c]
         assert sel.shape[0] == L // 100 and (sel[:, 2] == c).all()
-    print("GATHER_OK", flush=True)
 else:
     assert out is None
+# the exact-size point-to-point form (rows stay tensors; NCCL between GPUs, gloo here)
+table, first = [], 0
+for c in mine:
+    table.append((c, 1, first, lens[c] // 100)); first += lens[c] // 100
+got, merged = gather_rows_to_rank0(torch.from_numpy(rows), table)
+if rank == 0:
+    assert got.shape == (22, 8) and sorted(e[0] for e in merged) == [0, 1, 2, 3, 4]
+    for cid, kind, a, cnt in merged:
+        blk = got[a:a + cnt].numpy()
+        assert kind == 1 and cnt == lens[cid] // 100 and (blk[:, 2] == cid).all()
+        assert (blk[:, 0] == np.arange(cnt) * 10 + cid).all()
+    print("GATHER_OK", flush=True)
+else:
+    assert got is None and merged is None
 dist.destroy_process_group()
 """
 

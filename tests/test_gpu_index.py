@@ -65,7 +65,15 @@ def _check_index(DeviceIndex, oracle, text: bytes, occ_rate=128, searches=True):
             L = int(rng.integers(1, min(14, n) + 1))
             p = int(rng.integers(0, n - L + 1))
             pats.append(text[p:p + L])
-        sp, ep = ix.backward_search_batch(pats)
+        sp, ep = ix.backward_search_batch(pats)            # packed rank blocks (the default path)
+        assert ix.use_packed and ix._fm is not None
+        ix.use_packed = False                              # the byte BWT + Occ rows must agree
+        sp_b, ep_b = ix.backward_search_batch(pats)
+        ix.use_packed = True
+        assert np.array_equal(sp, sp_b) and np.array_equal(ep, ep_b), "packed and byte search differ"
+        ix.build_ftab(min(4, max(1, n // 8)))              # seeded by a k-mer interval table: same answers
+        sp_f, ep_f = ix.backward_search_batch(pats)
+        assert np.array_equal(sp, sp_f) and np.array_equal(ep, ep_f), "k-mer table changes the answers"
         stride = max(len(p) for p in pats)
         mat = np.zeros((len(pats), stride), np.uint8)
         lens = np.array([len(p) for p in pats], np.int32)
@@ -144,9 +152,11 @@ def test_motif_sweep_matches_batched_search(DeviceIndex, oracle):
     assert np.array_equal(sp.astype(np.int64), osp) and np.array_equal(ep.astype(np.int64), oep)
 
 
-def test_rank_probes(DeviceIndex, oracle):
+@pytest.mark.parametrize("packed", [True, False], ids=["packed", "bytes"])
+def test_rank_probes(DeviceIndex, oracle, packed):
     text = gen_contig(5000, 2).tobytes() + b"$"
     ix = DeviceIndex(text, build_kmer=False)
+    ix.use_packed = packed
     oi = oracle.OracleIndex(text)
     rng = np.random.default_rng(0)
     codes = [int(x) for x in rng.choice([36, 65, 67, 71, 84, 78, 0, 255], 500)]
@@ -156,6 +166,62 @@ def test_rank_probes(DeviceIndex, oracle):
         pp = min(max(p, 0), len(text))
         want = int(np.count_nonzero(oi.bwt[:pp] == c))
         assert g == want
+
+
+def _rank_texts():
+    rng = np.random.default_rng(5)
+    rnd = lambda n: bytes(b"ACGT"[x] for x in rng.integers(0, 4, n))
+    return [
+        ("n192", rnd(191) + b"$"),                      # n a multiple of the block size: header-only tail block
+        ("n384", rnd(383) + b"$"),
+        ("n193", rnd(192) + b"$"),
+        ("N_blocks", rnd(700) + b"N" * 900 + rnd(333) + b"N" * 5 + rnd(100) + b"$"),
+        ("all_bytes", bytes(int(x) for x in rng.integers(0, 256, 4000))),
+        ("iupac_lower", (b"ACGTRYKMSWBDHVNacgtn" * 97) + b"$"),
+        ("allA", b"A" * 1000 + b"$"),
+        ("no_acgt", b"NNNNRYRYNN" * 50 + b"$"),
+    ]
+
+
+@pytest.mark.parametrize("name,text", _rank_texts(), ids=[c[0] for c in _rank_texts()])
+def test_packed_rank_every_byte_every_position(DeviceIndex, oracle, name, text):
+    """bwtk_fm_rank_batch == a prefix count of the oracle's BWT for every byte value that occurs (plus two
+    that do not) at every position 0..n, and the packed / byte / k-mer-seeded searches agree."""
+    ix = DeviceIndex(text, build_kmer=False)
+    oi = oracle.OracleIndex(text)
+    n = len(text)
+    present = sorted(set(text))
+    absent = [b for b in (0, 35, 90, 255) if b not in present][:2]
+    codes, pos = [], []
+    for c in present[:24] + absent:
+        codes += [c] * (n + 1)
+        pos += list(range(n + 1))
+    got = ix.rank_batch(codes, pos).reshape(-1, n + 1)
+    for row, c in zip(got, present[:24] + absent):
+        want = np.concatenate(([0], np.cumsum(oi.bwt == c)))
+        assert np.array_equal(row, want), f"rank({c}, .) differs"
+    rng = np.random.default_rng(n)
+    alphabet = np.array(present + absent, np.uint8)
+    nq = 3000
+    lens = rng.integers(0, 9, nq).astype(np.int32)
+    pats = alphabet[rng.integers(0, alphabet.size, (nq, 8))]
+    for i in range(0, nq, 2):                               # half of the queries are substrings of the text
+        L = int(min(lens[i], n))
+        a = int(rng.integers(0, n - L + 1))
+        pats[i, :L] = np.frombuffer(text[a:a + L], np.uint8)
+        lens[i] = L
+    want_sp, want_ep = oi.backward_search_batch(np.ascontiguousarray(pats), lens)
+    plist = [bytes(pats[i, : lens[i]]) for i in range(nq)]
+    for mode in ("packed", "bytes", "ftab"):
+        ix.use_packed = mode != "bytes"
+        if mode == "ftab":
+            ix.build_ftab(3)
+        sp, ep = ix.backward_search_batch(plist)
+        assert np.array_equal(sp.astype(np.int64), want_sp) and np.array_equal(ep.astype(np.int64), want_ep), mode
+    sp, ep = ix.motif_sweep(5)
+    ix.use_packed = False
+    sp_b, ep_b = ix.motif_sweep(5)
+    assert np.array_equal(sp.cpu().numpy(), sp_b.cpu().numpy()) and np.array_equal(ep.cpu().numpy(), ep_b.cpu().numpy())
 
 
 def test_standalone_entry_points(oracle):
@@ -221,9 +287,9 @@ def test_index_pipeline_overlapped_builds(DeviceIndex, oracle):
         tickets.append(pipe.submit(host))
         if i >= 1:   # consume the previous one while this one is in flight
             r = pipe.result(tickets[i - 1])
-            results[i - 1] = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items() if k != "occ"}
+            results[i - 1] = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items()}
     r = pipe.result(tickets[-1])
-    results[len(texts) - 1] = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items() if k != "occ"}
+    results[len(texts) - 1] = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in r.items()}
     for i, t in enumerate(texts):
         oi = oracle.OracleIndex(t)
         assert results[i]["n"] == len(t)
@@ -231,6 +297,10 @@ def test_index_pipeline_overlapped_builds(DeviceIndex, oracle):
         assert np.array_equal(results[i]["bwt"], oi.bwt), f"contig {i}: BWT"
         assert np.array_equal(results[i]["lcp"], oi.lcp()), f"contig {i}: LCP"
         assert np.array_equal(results[i]["totals"], oi.totals)
+        occ = results[i]["occ"].cpu().numpy()      # a right-shaped copy, not the slot's live buffer
+        assert occ.shape == (len(oi.occ), results[i]["ncp"])
+        for code, cp in oi.occ.items():
+            assert np.array_equal(occ[results[i]["row_of_code"][code], : cp.size], cp), f"contig {i}: Occ[{code}]"
     with pytest.raises(_lib.BwtkError):
         pipe.result(tickets[0])            # slot reused
     with pytest.raises(_lib.BwtkError):
