@@ -273,8 +273,24 @@ def fm_section(torch, L, lib, dev, n, bwt, occ, ncp, totals, row, flush, args):
                                          "frac": round(nq * (sect * 64 + 18) / (ms * 1e-3) / 1e9 / peak, 4),
                                          "note": "packed index (62 MB of blocks for chr1) is L2-resident: frac may exceed 1; "
                                                  "see profiles/ for lts__t_sectors and the L2 hit rate"}}
-    # parity spot check inside the bench: interval sizes of the first 2^16 queries sum like a direct recount
-    del pats, lens, sp, ep
+    want_sp, want_ep = sp.clone(), ep.clone()
+    variants = {}
+    for name, attrs in (("thread_per_query", {"thread_per_query": True}), ("no_l2_window", {"l2_persist": False}),
+                        ("byte_bwt_occ_rows", {"use_packed": False})):
+        for k, v in attrs.items():
+            setattr(rep, k, v)
+        vms = timed(run_batch, reps=2)
+        same = bool(torch.equal(sp, want_sp) and torch.equal(ep, want_ep))
+        variants[name] = {"ms": round(vms, 4), "queries_per_s": round(nq / (vms * 1e-3), 1), "same_answers": same}
+        for k in attrs:
+            setattr(rep, k, getattr(type(rep), k))
+    rep.build_ftab(8)
+    vms = timed(run_batch, reps=2)
+    variants["kmer_table_8"] = {"ms": round(vms, 4), "queries_per_s": round(nq / (vms * 1e-3), 1),
+                                "same_answers": bool(torch.equal(sp, want_sp) and torch.equal(ep, want_ep)),
+                                "note": "patterns start from the interval of their last 8 characters (65 536-entry table): 2 LF steps"}
+    out["random_10mers"]["variants"] = variants
+    del pats, lens, sp, ep, want_sp, want_ep
     return out
 
 
@@ -318,9 +334,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     my_bases = sum(lengths[i] for i in mine)
     max_n = max([lengths[i] for i in mine] + [2000]) + 1
-    arena_rows = my_bases // 14 + 65536 * max(len(mine), 1)
+    arena_rows = my_bases // 14 + 262144 * max(len(mine), 1)   # small contigs: the period scan's raw rows dominate
     scanner = GenomeScanner(max_n, arena_rows, device=dev)
-    all_rows_cap = total_bases // 14 + 65536 * len(lengths)
+    all_rows_cap = total_bases // 14 + 262144 * len(lengths)
     gather_buf = torch.empty((all_rows_cap, 8), dtype=torch.int32, device=dev) if (rank == 0 and world > 1) else None
     kind_id = {k: j for j, k in enumerate(KINDS)}
 

@@ -82,6 +82,7 @@ _SIGS = {
 EXPORTS = tuple(_SIGS.keys())
 
 FM_L2_PERSIST = 1
+FM_THREAD_PER_QUERY = 2
 
 
 class FmIndex(C.Structure):

@@ -313,6 +313,109 @@ __global__ void __launch_bounds__(256)
     ep_out[q] = ep;
 }
 
+// Warp-cooperative form: the 32 lanes own 32 queries, but every rank is answered by a GROUP OF FOUR
+// lanes that load one 16-byte quarter of the 64-byte block each, so a warp-wide load instruction
+// touches 8 lines (8 complete blocks) instead of 32 and a rank costs one L1 wavefront instead of
+// 3.3 (header, first sector's symbols, and for two positions in three the second sector): the
+// thread-per-query kernel is bound by exactly that (ncu: L1tex wavefronts; B300_MICROARCH "LDG").
+// The group serves its four members in turn: one shuffle broadcasts (position, symbol), the quarter
+// counts are summed with two xor-shuffles.  Lanes whose quarter lies past the position, and groups
+// whose member is finished or is on a non-ACGT character, issue no load.
+__global__ void __launch_bounds__(256)
+    search_coop_kernel(Packed ix, const uint8_t *__restrict__ pats, int64_t stride, const int32_t *__restrict__ lens,
+                       int64_t nq, int32_t *__restrict__ sp_out, int32_t *__restrict__ ep_out)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, g = lane & 3u;
+    const bool have = q < nq;
+    const int m = have ? lens[q] : 0;
+    const uint8_t *p = pats + (have ? q : 0) * stride;
+    int sp = 0, ep = ix.n - 1;
+    int i = m - 1;
+    bool seeded = false;
+    if (have && ix.ftab_k > 0 && m >= ix.ftab_k) {
+        uint32_t v = 0;
+        bool ok = true;
+        for (int j = 0; j < ix.ftab_k; j++) {
+            const int c2 = code2_of(__ldg(p + m - ix.ftab_k + j));
+            ok = ok && c2 >= 0;
+            v = (v << 2) | (uint32_t)(c2 & 3);
+        }
+        if (ok) {
+            sp = __ldg(ix.ftab_sp + v);
+            ep = __ldg(ix.ftab_ep + v);
+            i = m - ix.ftab_k - 1;
+            if (sp < 0) i = -1;
+            seeded = true;
+        }
+    }
+    if (have && !seeded && m > 0) {
+        const int c = __ldg(p + m - 1);
+        const long long t = __ldg(ix.tot + c);
+        if (t == 0) { sp = ep = -1; i = -1; }
+        else { sp = (int)__ldg(ix.C + c); ep = sp + (int)t - 1; i = m - 2; }
+    }
+    while (__any_sync(0xffffffffu, i >= 0)) {
+        // this lane's request for the step: two positions and a 2-bit symbol, or nothing
+        uint32_t msg0 = 0xffffffffu, msg1 = 0xffffffffu;
+        int c2 = -1;
+        if (i >= 0) {
+            const int c = __ldg(p + i);
+            c2 = code2_of(c);
+            if (c2 >= 0) {
+                if (ix.tot4[c2] == 0) { sp = ep = -1; i = -1; c2 = -1; }
+                else {
+                    msg0 = (uint32_t)sp | ((uint32_t)c2 << 30);
+                    msg1 = (uint32_t)(ep + 1) | ((uint32_t)c2 << 30);
+                }
+            } else {
+                // '$', N, IUPAC ...: binary search in the exception lists, by the lane itself
+                if (__ldg(ix.tot + c) == 0) { sp = ep = -1; i = -1; }
+                else {
+                    const int cc = (int)__ldg(ix.C + c);
+                    const int a = rank_any(ix, c, sp), b = rank_any(ix, c, (int64_t)ep + 1);
+                    sp = cc + a;
+                    ep = cc + b - 1;
+                    if (sp > ep) { sp = ep = -1; i = -1; } else i--;
+                }
+            }
+        }
+        int r0 = 0, r1 = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const unsigned owner = (lane & ~3u) | (unsigned)(t >> 1);
+            const uint32_t msg = __shfl_sync(0xffffffffu, (t & 1) ? msg1 : msg0, owner);
+            int part = 0;
+            if (msg != 0xffffffffu) {
+                const uint32_t pos = msg & 0x3fffffffu, s2 = msg >> 30;
+                const uint32_t blk = pos / BLK;
+                const int off = (int)(pos - blk * BLK);
+                if (g == 0 || off > 64 * ((int)g - 1)) {
+                    const uint4 v = __ldg(ix.blocks + (size_t)blk * 4 + g);
+                    if (g == 0) {
+                        part = (int)(s2 == 0 ? (v.x & 0x3fffffffu) : s2 == 1 ? v.y : s2 == 2 ? v.z : v.w);
+                        if (s2 == 0 && (v.x >> 31) && off > 0) part -= exceptions_in(ix, blk * BLK, pos);
+                    } else {
+                        part = count_vec(v, 0x55555555u * s2, off - 64 * ((int)g - 1));
+                    }
+                }
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (lane == owner) { if (t & 1) r1 = part; else r0 = part; }
+        }
+        if (c2 >= 0) {
+            sp = ix.C4[c2] + r0;
+            ep = ix.C4[c2] + r1 - 1;
+            if (sp > ep) { sp = ep = -1; i = -1; } else i--;
+        }
+    }
+    if (have) {
+        sp_out[q] = sp;
+        ep_out[q] = ep;
+    }
+}
+
 __global__ void __launch_bounds__(256)
     rank_kernel(Packed ix, const int32_t *__restrict__ codes, const int64_t *__restrict__ pos, int64_t nq,
                 int64_t *__restrict__ out)
@@ -520,7 +623,11 @@ extern "C" int32_t bwtk_fm_search_batch(const bwtk_fm_index *fx, const uint8_t *
     if (win) l2_window(st, fx->d_blocks, (size_t)bwtk_fm_pack_bytes(fx->n), true);
     {
         prof::Scope ps("fm_search_kernel", nq * (stride + 12), st);
-        fmp::search_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(ix, d_pats, stride, d_lens, nq, d_sp, d_ep);
+        if (flags & BWTK_FM_THREAD_PER_QUERY)
+            fmp::search_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(ix, d_pats, stride, d_lens, nq, d_sp, d_ep);
+        else
+            fmp::search_coop_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(ix, d_pats, stride, d_lens, nq, d_sp,
+                                                                                d_ep);
         count_launch();
     }
     cudaError_t e = cudaGetLastError();

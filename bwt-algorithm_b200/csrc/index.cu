@@ -118,7 +118,8 @@ void end(cudaStream_t st)
 
 int64_t sa_core_workspace_bytes(int64_t n);
 int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_t *d_sa, int32_t *d_isa_out,
-                  void *d_ws, int64_t ws_bytes, int64_t *h_stats, cudaStream_t st, const uint32_t **d_skey0_out);
+                  void *d_ws, int64_t ws_bytes, int64_t *h_stats, cudaStream_t st, const uint32_t **d_skey0_out,
+                  void **d_free_out, int64_t *free_bytes_out);
 
 // ------------------------------------------------------------------ histogram
 // out[0..255] = byte counts, out[256] = the last byte of the text
@@ -426,106 +427,10 @@ static int launch_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n,
     return BWTK_OK;
 }
 
-// ------------------------------------------------------------------ LCP
-// lcp[j] = LCP(suffix sa[j-1], suffix sa[j]) by direct comparison of bit-packed
-// windows (64 stream bits per step).  `slack` = 1 for the ACGT$ layout (the
-// sentinel shares a code with 'A', and being unique it can never match), else 0.
-__global__ void __launch_bounds__(256)
-    lcp_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ sa, int64_t n, int bits,
-               int slack, int32_t *__restrict__ lcp)
-{
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    if (j == 0) { lcp[0] = 0; return; }
-    int64_t a = __ldg(sa + j - 1), b = __ldg(sa + j);
-    int64_t limit = n - slack - (a > b ? a : b);
-    int64_t h = 0;
-    const int per = 64 / bits;
-    while (h < limit) {
-        uint64_t x = window64(packed, (a + h) * bits) ^ window64(packed, (b + h) * bits);
-        if (x) {
-            h += __clzll((long long)x) / bits;
-            break;
-        }
-        h += per;
-    }
-    lcp[j] = (int32_t)(h < limit ? h : limit);
-}
-
-// Same result with the sorted round-0 keys at hand (fused index build): skey[j] is the
-// first S symbols of suffix sa[j], so wherever two neighbouring keys differ the LCP is the
-// length of their common bit prefix -- two coalesced reads instead of six gathers from the
-// packed text.  Pairs with equal keys (the suffixes that stayed ambiguous after round 0) and
-// the few suffixes whose window touches the end of the text are compacted into shared memory
-// and compared window by window by all threads of the CTA.
-constexpr int LCPK_THREADS = 256;
-constexpr int LCPK_ITEMS = 8;
-
-__global__ void __launch_bounds__(LCPK_THREADS)
-    lcp_keys_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ sa,
-                    const uint32_t *__restrict__ skey, int64_t n, int bits, int slack, int32_t *__restrict__ lcp)
-{
-    __shared__ int s_list[LCPK_THREADS * LCPK_ITEMS];
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * (LCPK_THREADS * LCPK_ITEMS);
-    const int S = 32 / bits;
-#pragma unroll
-    for (int it = 0; it < LCPK_ITEMS; it++) {
-        const int local = it * LCPK_THREADS + threadIdx.x;
-        const int64_t j = base + local;
-        bool slow = false;
-        if (j < n) {
-            if (j == 0) {
-                lcp[0] = 0;
-            } else {
-                const uint32_t x = __ldg(skey + j - 1) ^ __ldg(skey + j);
-                const int64_t a = __ldg(sa + j - 1), b = __ldg(sa + j);
-                if (x != 0u && (a > b ? a : b) < n - S) lcp[j] = __clz((int)x) / bits;
-                else slow = true;
-            }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, slow);
-        if (bal) {
-            int at = 0;
-            if ((threadIdx.x & 31) == 0) at = atomicAdd(&s_cnt, __popc(bal));
-            at = __shfl_sync(0xffffffffu, at, 0);
-            if (slow) s_list[at + __popc(bal & lanemask_lt())] = local;
-        }
-    }
-    __syncthreads();
-    const int cnt = s_cnt;
-    const int per = 64 / bits;
-    for (int q = threadIdx.x; q < cnt; q += LCPK_THREADS) {
-        const int64_t j = base + s_list[q];
-        const int64_t a = __ldg(sa + j - 1), b = __ldg(sa + j);
-        const int64_t limit = n - slack - (a > b ? a : b);
-        int64_t h = 0;
-        while (h < limit) {
-            uint64_t x = window64(packed, (a + h) * bits) ^ window64(packed, (b + h) * bits);
-            if (x) {
-                h += __clzll((long long)x) / bits;
-                break;
-            }
-            h += per;
-        }
-        lcp[j] = (int32_t)(h < limit ? h : limit);
-    }
-}
-
-static int launch_lcp(const uint32_t *packed, const int32_t *d_sa, const uint32_t *d_skey0, int64_t n, int bits,
-                      bool fast, int32_t *d_lcp, cudaStream_t st)
-{
-    prof::Scope ps("lcp_kernel", n * 8, st);
-    if (d_skey0)
-        lcp_keys_kernel<<<(unsigned)ceil_div(n, LCPK_THREADS * LCPK_ITEMS), LCPK_THREADS, 0, st>>>(
-            packed, d_sa, d_skey0, n, bits, fast ? 1 : 0, d_lcp);
-    else
-        lcp_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(packed, d_sa, n, bits, fast ? 1 : 0, d_lcp);
-    BWTK_LAUNCH_CHECK();
-    return BWTK_OK;
-}
+// ------------------------------------------------------------------ LCP (lcp.cu)
+int64_t lcp_scratch_bytes(int64_t n);
+int launch_lcp(const uint32_t *packed, const int32_t *d_sa, const uint32_t *d_skey0, int64_t n, int bits, bool fast,
+               int32_t *d_lcp, void *d_scratch, int64_t scratch_bytes, cudaStream_t st);
 
 }  // namespace bwtk
 
@@ -678,7 +583,7 @@ extern "C" int32_t bwtk_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int6
 extern "C" int64_t bwtk_lcp_workspace_bytes(int64_t n)
 {
     if (n < 1) n = 1;
-    return align_up(packed_words(n, 8) * 4, 256) + 8192;
+    return align_up(packed_words(n, 8) * 4, 256) + 8192 + lcp_scratch_bytes(n);
 }
 
 extern "C" int32_t bwtk_lcp_build(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int32_t *d_lcp,
@@ -699,7 +604,8 @@ extern "C" int32_t bwtk_lcp_build(const uint8_t *d_text, const int32_t *d_sa, in
     bool fast;
     int rc = prepare_text(d_text, n, packed, d_hist, totals, &bits, &fast, st);
     if (rc) return rc;
-    return launch_lcp(packed, d_sa, nullptr, n, bits, fast, d_lcp, st);
+    c.off = align_up(c.off, 256);
+    return launch_lcp(packed, d_sa, nullptr, n, bits, fast, d_lcp, (char *)d_ws + c.off, ws_bytes - c.off, st);
 }
 
 // ---- fused index build: a3 + a4 + a5 + a6 + a10 with one histogram, one packed
@@ -751,7 +657,10 @@ extern "C" int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t oc
     }
     c.off = align_up(c.off, 256);
     const uint32_t *d_skey0 = nullptr;
-    rc = sa_build_core(packed, n, bits, fast, d_sa, d_isa, (char *)d_ws + c.off, ws_bytes - c.off, h_stats, st, &d_skey0);
+    void *d_free = nullptr;          // the part of the suffix-sort workspace that is dead once the SA stands
+    int64_t free_bytes = 0;
+    rc = sa_build_core(packed, n, bits, fast, d_sa, d_isa, (char *)d_ws + c.off, ws_bytes - c.off, h_stats, st, &d_skey0,
+                       &d_free, &free_bytes);
     if (rc) return rc;
     if (h_stats) h_stats[7] = nrows;
     if (d_bwt && d_occ) {
@@ -759,7 +668,7 @@ extern "C" int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t oc
         if (rc) return rc;
     }
     if (d_lcp) {
-        rc = launch_lcp(packed, d_sa, d_skey0, n, bits, fast, d_lcp, st);
+        rc = launch_lcp(packed, d_sa, d_skey0, n, bits, fast, d_lcp, d_free, free_bytes, st);
         if (rc) return rc;
     }
     return BWTK_OK;

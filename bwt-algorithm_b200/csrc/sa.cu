@@ -489,10 +489,12 @@ int64_t sa_core_workspace_bytes(int64_t n)
 // Suffix array of the text whose packed form (bits per symbol, `fast` = ACGT$
 // layout) is already on the device.  Synchronises the stream.
 int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_t *d_sa, int32_t *d_isa_out,
-                  void *d_ws, int64_t ws_bytes, int64_t *h_stats, cudaStream_t st, const uint32_t **d_skey0_out)
+                  void *d_ws, int64_t ws_bytes, int64_t *h_stats, cudaStream_t st, const uint32_t **d_skey0_out,
+                  void **d_free_out, int64_t *free_bytes_out)
 {
     if (h_stats) memset(h_stats, 0, 8 * sizeof(int64_t));
     if (d_skey0_out) *d_skey0_out = nullptr;
+    if (d_free_out) { *d_free_out = nullptr; *free_bytes_out = 0; }
     BWTK_REQUIRE((((uintptr_t)d_sa | (uintptr_t)d_ws) & 15) == 0, "d_sa and the workspace must be 16-byte aligned");
     if (ws_bytes < sa_core_workspace_bytes(n)) {
         set_error("sa workspace: need %lld bytes, got %lld", (long long)sa_core_workspace_bytes(n),
@@ -551,6 +553,12 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     // key of the suffix at every SA position (later rounds only permute suffixes inside a
     // group of equal keys); stays valid until the caller reuses the workspace
     if (d_skey0_out) *d_skey0_out = skey32;
+    if (d_free_out) {
+        // everything from the second key buffer on is scratch for the caller once this function returns
+        // (28 n bytes + the radix workspace: enough for the LCP's deep-pair pass, lcp.cu)
+        *d_free_out = keyB;
+        *free_bytes_out = (int64_t)((char *)d_ws + ws_bytes - (char *)keyB);
+    }
     uint32_t *sval = in_first ? val0 : val1;
     int32_t *pos_in = pos0, *pos_out = pos1;
     uint32_t *suf_other = in_first ? val1 : val0;  // free value buffer receives the active suffixes
@@ -720,5 +728,5 @@ extern "C" int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa
     if (rc) return rc;
     c.off = align_up(c.off, 256);
     return sa_build_core(packed, n, bits, fast, d_sa, d_isa_out, (char *)d_ws + c.off, ws_bytes - c.off, h_stats, st,
-                         nullptr);
+                         nullptr, nullptr, nullptr);
 }

@@ -35,6 +35,8 @@ class _FMSearch:
     ftab_k = 0
     #: keep the rank blocks resident in L2 while a batch streams through
     l2_persist = True
+    #: one thread per query instead of four lanes sharing every block load (kept for A/B measurements)
+    thread_per_query = False
 
     def ensure_packed(self):
         """Builds the packed search index (bwtk_fm_pack) from the BWT bytes on first use."""
@@ -85,7 +87,7 @@ class _FMSearch:
         self.ftab_k = int(k)
 
     def _flags(self) -> int:
-        return _lib.FM_L2_PERSIST if self.l2_persist else 0
+        return (_lib.FM_L2_PERSIST if self.l2_persist else 0) | (_lib.FM_THREAD_PER_QUERY if self.thread_per_query else 0)
 
     # ------------------------------------------------------------------ a8 / a9
     def search_device(self, d_pats, stride: int, d_lens, nq: int):

@@ -175,6 +175,7 @@ typedef struct bwtk_fm_index {
     int32_t ftab_k;                /* 0 = no table */
 } bwtk_fm_index;
 #define BWTK_FM_L2_PERSIST 1       /* flags: keep the rank blocks resident in L2 (access policy window) */
+#define BWTK_FM_THREAD_PER_QUERY 2 /* flags: one thread per query (default: four lanes share every block load) */
 int64_t bwtk_fm_pack_bytes(int64_t n);
 int64_t bwtk_fm_pack_workspace_bytes(int64_t n, int64_t n_exc);
 int32_t bwtk_fm_pack(const uint8_t *d_bwt, int64_t n, const int64_t *h_totals, void *d_blocks,

@@ -56,7 +56,7 @@ def test_genome_scanner_rows_match_oracle(oracle, where):
         ins = [torch.from_numpy(np.frombuffer(t, np.uint8).copy()).pin_memory() for t in texts]
     else:
         ins = [torch.from_numpy(np.frombuffer(t, np.uint8).copy()).cuda() for t in texts]
-    sc = GenomeScanner(max(len(t) for t in texts), arena_rows=200_000)
+    sc = GenomeScanner(max(len(t) for t in texts), arena_rows=800_000)
     for rep in range(2):                                  # a second pass reuses every buffer and event
         res = sc.scan(ins, ids=list(range(10, 10 + len(texts))), download=(where == "host"))
         assert [r.contig for r in res] == list(range(10, 10 + len(texts)))
@@ -92,7 +92,7 @@ texts = _contigs()
 bins = sharding.lpt_partition([len(t) for t in texts], world)
 mine = bins[rank]
 pin = lambda t: torch.from_numpy(np.frombuffer(t, np.uint8).copy()).pin_memory()
-sc = GenomeScanner(max(len(t) for t in texts), arena_rows=400_000, device=dev)
+sc = GenomeScanner(max(len(t) for t in texts), arena_rows=800_000, device=dev)
 res = sc.scan([pin(texts[i]) for i in mine], ids=mine)
 table = [(r.contig, KINDS.index(k), a, c) for r in res for k, (a, c) in r.span.items()]
 rows, merged = sharding.gather_rows_to_rank0(sc.arena[: sc.used], table)

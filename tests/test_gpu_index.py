@@ -71,6 +71,10 @@ def _check_index(DeviceIndex, oracle, text: bytes, occ_rate=128, searches=True):
         sp_b, ep_b = ix.backward_search_batch(pats)
         ix.use_packed = True
         assert np.array_equal(sp, sp_b) and np.array_equal(ep, ep_b), "packed and byte search differ"
+        ix.thread_per_query = True
+        sp_t, ep_t = ix.backward_search_batch(pats)
+        ix.thread_per_query = False
+        assert np.array_equal(sp, sp_t) and np.array_equal(ep, ep_t), "cooperative and per-thread search differ"
         ix.build_ftab(min(4, max(1, n // 8)))              # seeded by a k-mer interval table: same answers
         sp_f, ep_f = ix.backward_search_batch(pats)
         assert np.array_equal(sp, sp_f) and np.array_equal(ep, ep_f), "k-mer table changes the answers"
@@ -212,8 +216,10 @@ def test_packed_rank_every_byte_every_position(DeviceIndex, oracle, name, text):
         lens[i] = L
     want_sp, want_ep = oi.backward_search_batch(np.ascontiguousarray(pats), lens)
     plist = [bytes(pats[i, : lens[i]]) for i in range(nq)]
-    for mode in ("packed", "bytes", "ftab"):
+    for mode in ("packed", "thread_per_query", "no_l2_window", "bytes", "ftab"):
         ix.use_packed = mode != "bytes"
+        ix.thread_per_query = mode == "thread_per_query"
+        ix.l2_persist = mode != "no_l2_window"
         if mode == "ftab":
             ix.build_ftab(3)
         sp, ep = ix.backward_search_batch(plist)
@@ -372,3 +378,100 @@ def test_bwtcore_load_index_matches_fresh_build(tmp_path):
         assert back.backward_search(pat) == fresh.backward_search(pat)
         assert back.locate_positions(pat) == fresh.locate_positions(pat)
     assert back.get_kmer_positions("ACGTACGT") == fresh.get_kmer_positions("ACGTACGT")
+
+
+# ---- LCP with a bounded worst case (lcp.cu: direct compare up to a budget, then the Phi/PLCP-ordered pass) ----
+def _naive_lcp_check(text: bytes, sa: np.ndarray, lcp: np.ndarray, rng, probes=4000):
+    """LCP spot check without the oracle's O(n) pass holding the whole table: exact at `probes` SA positions
+    (vectorised compare of the two suffixes) + the extremes."""
+    t = np.frombuffer(text, np.uint8)
+    n = t.size
+    idx = np.unique(np.concatenate([rng.integers(1, n, probes), np.argsort(lcp)[-50:], [1, n - 1]]))
+    for j in idx:
+        if j == 0:
+            continue
+        a, b = int(sa[j - 1]), int(sa[j])
+        m = n - max(a, b)
+        x = np.flatnonzero(t[a:a + m] != t[b:b + m])
+        want = int(x[0]) if x.size else m
+        assert lcp[j] == want, f"lcp[{j}] = {lcp[j]}, expected {want} (suffixes {a}, {b})"
+
+
+def _deep_texts():
+    rng = np.random.default_rng(77)
+    rnd = lambda n: bytes(b"ACGT"[x] for x in rng.integers(0, 4, n))
+    body = rnd(120_000)
+    return [
+        ("three_copies_of_3000", rnd(3000) * 3 + b"$"),                       # LCP up to 6000 > the 2048-base budget
+        ("N_block_50k_in_120k", body[:40_000] + b"N" * 50_000 + body[40_000:70_000] + b"$"),
+        ("rnd1300_x_60", rnd(1300) * 60 + b"$"),
+        ("allA_100k", b"A" * 100_000 + b"$"),
+        ("two_long_copies", body[:30_000] + rnd(10) + body[:30_000] + rnd(5) + body[5_000:25_000] + b"$"),
+        ("deep_at_chunk_edges", (rnd(2500) + b"G") * 37 + rnd(99) + b"$"),
+    ]
+
+
+@pytest.mark.parametrize("name,text", _deep_texts(), ids=[c[0] for c in _deep_texts()])
+def test_lcp_deep_pairs_match_oracle(DeviceIndex, oracle, name, text):
+    import torch
+
+    from bwt_algorithm_b200 import _lib
+
+    ix = DeviceIndex(text, build_kmer=False, build_lcp=True)
+    oi = oracle.OracleIndex(text)
+    want = oi.lcp()
+    assert int(want.max()) > 2048, "the case must reach the deep-pair pass"
+    assert np.array_equal(ix.sa.cpu().numpy(), oi.sa)
+    assert np.array_equal(ix.lcp.cpu().numpy(), want), "fused LCP differs"
+    # the stand-alone entry point (no round-0 keys: every pair goes through the window compare)
+    L = _lib.lib()
+    n = len(text)
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    ws = torch.empty(int(L.bwtk_lcp_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.bwtk_lcp_build(ix.text.data_ptr(), ix.sa.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                _lib.stream_ptr()), "lcp_build")
+    assert np.array_equal(out.cpu().numpy(), want), "stand-alone LCP differs"
+
+
+def test_lcp_worst_cases_stay_bounded(DeviceIndex):
+    """a 2 Mb N block inside a 5 Mb contig, rnd(1300)*4000 and all-A 5 Mb -- exact (spot-checked
+    against a direct suffix compare) and the LCP stage within 3x the planted contig's time per base."""
+    import time
+
+    import torch
+
+    from bwt_algorithm_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    rnd = lambda n: np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)]
+    planted = gen_contig(5_000_000, 31)
+    nblock = planted.copy()
+    nblock[1_500_000:3_500_000] = ord("N")
+    cases = {"planted_5mb": planted, "N_block_2mb_in_5mb": nblock,
+             "rnd1300_x_4000": np.tile(rnd(1300), 4000), "allA_5mb": np.full(5_000_000, ord("A"), np.uint8)}
+    L = _lib.lib()
+    per_base = {}
+    for name, arr in cases.items():
+        text = arr.tobytes() + b"$"
+        ix = DeviceIndex(text, build_kmer=False, build_lcp=True)
+        n = len(text)
+        sa, lcp = ix.sa.cpu().numpy(), ix.lcp.cpu().numpy()
+        _naive_lcp_check(text, sa, lcp, np.random.default_rng(1))
+        if name != "planted_5mb":
+            assert int(lcp.max()) > 100_000
+        out = torch.empty(n, dtype=torch.int32, device="cuda")
+        ws = torch.empty(int(L.bwtk_lcp_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+        best = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _lib.check(L.bwtk_lcp_build(ix.text.data_ptr(), ix.sa.data_ptr(), n, out.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), _lib.stream_ptr()), "lcp_build")
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        assert np.array_equal(out.cpu().numpy(), lcp)
+        per_base[name] = best / n
+        del ix, out, ws
+    print("LCP seconds per base:", {k: f"{v:.3e}" for k, v in per_base.items()})
+    for name, v in per_base.items():
+        assert v <= 3.0 * per_base["planted_5mb"] + 2e-10, f"{name}: {v:.3e} s/base vs planted {per_base['planted_5mb']:.3e}"
