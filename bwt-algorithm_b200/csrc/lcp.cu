@@ -5,12 +5,13 @@
 //  1. Every pair is compared directly on the bit-packed text, 64 stream bits per step.  In the
 //     fused build the sorted round-0 keys are at hand, so wherever two neighbouring keys differ
 //     (94 % of a genome) the answer is the common bit prefix of two coalesced reads.  A pair gets a
-//     budget of DEEP_STEPS steps (2048 bases at 2 bits); what it has verified by then is stored as
+//     budget of DEEP_STEPS steps (256 bases at 2 bits); what it has verified by then is stored as
 //     a lower bound and the pair goes on a list.
 //  2. The listed ("deep") pairs are finished in TEXT order, which is where Kasai's invariant
 //     lives: with Phi(i) = sa[isa[i]-1] and PLCP[i] = LCP(i, Phi(i)), PLCP[i+k] >= PLCP[i] - k.
 //     The list is sorted by text position (radix sort of (sa[j], j)), cut into chunks, one warp per
-//     chunk, 32 entries per batch: every lane starts from max(own lower bound, previous exact value
+//     chunk (one CTA per chunk; its first entry is finished by all threads together, 8192 bases per
+//     step), 32 entries per batch: every lane starts from max(own lower bound, previous exact value
 //     - distance) and extends.  A lane that is still not done after another DEEP_STEPS is finished
 //     by the WHOLE warp (32 windows = 1024 bases per step), in list order, so that the entries
 //     behind it inherit its exact value; with that a jump of the PLCP by L costs L/1024 steps once
@@ -23,8 +24,9 @@ namespace bwtk {
 
 namespace {
 
-constexpr int DEEP_STEPS = 64;     // direct-compare budget of a pair, in 64-bit windows
-constexpr int DEEP_CHUNK = 2048;    // list entries per warp in stage 2
+constexpr int DEEP_STEPS = 8;      // direct-compare budget of a pair, in 64-bit windows
+constexpr int DEEP_CHUNK = 8192;   // list entries per CTA in stage 2
+constexpr int PLCP_THREADS = 256;
 constexpr int LCPK_THREADS = 256;
 constexpr int LCPK_ITEMS = 8;
 
@@ -174,19 +176,57 @@ __global__ void deep_keys_kernel(const int32_t *__restrict__ sa, const uint32_t 
     val[k] = j;
 }
 
-// pos[] ascending text positions i = sa[j] of the deep pairs, jdx[] their SA positions j
-__global__ void __launch_bounds__(128)
+// the same by a whole CTA (blockDim.x windows per step); every thread returns the exact value
+__device__ __forceinline__ int64_t extend_cta(const uint32_t *__restrict__ packed, int64_t a, int64_t b, int64_t limit,
+                                              int bits, int64_t h, unsigned long long *s_best)
+{
+    const int per = 64 / bits;
+    const unsigned long long NONE = ~0ull;
+    while (true) {
+        if (threadIdx.x == 0) *s_best = NONE;
+        __syncthreads();
+        const int64_t off = h + (int64_t)threadIdx.x * per;
+        uint64_t x = 0;
+        if (off < limit) x = window64(packed, (a + off) * bits) ^ window64(packed, (b + off) * bits);
+        if (off >= limit || x != 0) {
+            int64_t mine = off >= limit ? limit : off + __clzll((long long)x) / bits;
+            if (mine > limit) mine = limit;
+            atomicMin(s_best, (unsigned long long)mine);
+        }
+        __syncthreads();
+        const unsigned long long best = *s_best;
+        __syncthreads();
+        if (best != NONE) return (int64_t)best;
+        h += (int64_t)blockDim.x * per;
+    }
+}
+
+// pos[] ascending text positions i = sa[j] of the deep pairs, jdx[] their SA positions j.
+// One CTA per DEEP_CHUNK list entries: all warps finish the chunk's first entry together (a start from
+// scratch can be megabases deep), then every warp walks its own slice, 32 entries per batch, carrying
+// the previous exact value; the chunk's first value bounds every slice's first batch.
+__global__ void __launch_bounds__(PLCP_THREADS)
     plcp_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ sa, const uint32_t *__restrict__ pos,
                 const uint32_t *__restrict__ jdx, int64_t m, int64_t n, int bits, int slack,
                 int32_t *__restrict__ lcp)
 {
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ unsigned long long s_best;
     const unsigned lane = lane_id();
-    const int64_t e0 = warp * DEEP_CHUNK;
-    if (e0 >= m) return;
-    const int64_t e1 = e0 + DEEP_CHUNK < m ? e0 + DEEP_CHUNK : m;
-    bool have_carry = false;
-    int64_t carry_i = 0, carry_h = 0;
+    const int warp = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * DEEP_CHUNK;
+    if (c0 >= m) return;
+    int64_t carry_i, carry_h;
+    {
+        const int64_t i = __ldg(pos + c0), j = __ldg(jdx + c0);
+        const int64_t a = __ldg(sa + j - 1);
+        const int64_t limit = n - slack - (a > i ? a : i);
+        carry_i = i;
+        carry_h = extend_cta(packed, a, i, limit, bits, lcp[j], &s_best);
+        if (threadIdx.x == 0) lcp[j] = (int32_t)carry_h;
+    }
+    const int64_t e0 = c0 + (int64_t)warp * (DEEP_CHUNK / (PLCP_THREADS / 32));
+    const int64_t cend = c0 + DEEP_CHUNK < m ? c0 + DEEP_CHUNK : m;
+    const int64_t e1 = e0 + DEEP_CHUNK / (PLCP_THREADS / 32) < cend ? e0 + DEEP_CHUNK / (PLCP_THREADS / 32) : cend;
     for (int64_t base = e0; base < e1; base += 32) {
         const int64_t e = base + lane;
         const bool valid = e < e1;
@@ -196,11 +236,9 @@ __global__ void __launch_bounds__(128)
             j = __ldg(jdx + e);
             a = __ldg(sa + j - 1);                       // Phi(i)
             limit = n - slack - (a > i ? a : i);
-            h = lcp[j];                                  // what stage 1 verified
-            if (have_carry) {
-                const int64_t lb = carry_h - (i - carry_i);
-                if (lb > h) h = lb;
-            }
+            h = lcp[j];                                  // what stage 1 verified (or the chunk's first entry, exact)
+            const int64_t lb = carry_h - (i - carry_i);  // PLCP[i] >= PLCP[i'] - (i - i') for i' <= i
+            if (lb > h) h = lb;
         }
         bool done = !valid;
         if (valid) done = extend(packed, a, i, limit, bits, DEEP_STEPS, h);
@@ -215,9 +253,8 @@ __global__ void __launch_bounds__(128)
             const int64_t liml = __shfl_sync(0xffffffffu, limit, l);
             const int lp = l > 0 ? l - 1 : 0;
             int64_t ph = __shfl_sync(0xffffffffu, h, lp), pi = __shfl_sync(0xffffffffu, i, lp);
-            bool hp = l > 0;
-            if (l == 0) { ph = carry_h; pi = carry_i; hp = have_carry; }
-            if (hp && ph - (il - pi) > hl) hl = ph - (il - pi);
+            if (l == 0) { ph = carry_h; pi = carry_i; }
+            if (ph - (il - pi) > hl) hl = ph - (il - pi);
             const int64_t exact = extend_warp(packed, al, il, liml, bits, hl);
             if ((int)lane == l) { h = exact; done = true; }
         }
@@ -225,7 +262,6 @@ __global__ void __launch_bounds__(128)
         const int last = (int)((e1 - base < 32 ? e1 - base : 32) - 1);
         carry_h = __shfl_sync(0xffffffffu, h, last);
         carry_i = __shfl_sync(0xffffffffu, i, last);
-        have_carry = true;
     }
 }
 
@@ -288,8 +324,8 @@ int launch_lcp(const uint32_t *packed, const int32_t *d_sa, const uint32_t *d_sk
     const uint32_t *pos = in_first ? key0 : key1, *jdx = in_first ? val0 : val1;
     {
         prof::Scope ps("plcp_kernel", m * 16, st);
-        const int64_t warps = ceil_div(m, DEEP_CHUNK);
-        plcp_kernel<<<(unsigned)ceil_div(warps * 32, 128), 128, 0, st>>>(packed, d_sa, pos, jdx, m, n, bits, slack, d_lcp);
+        plcp_kernel<<<(unsigned)ceil_div(m, DEEP_CHUNK), PLCP_THREADS, 0, st>>>(packed, d_sa, pos, jdx, m, n, bits, slack,
+                                                                             d_lcp);
         BWTK_LAUNCH_CHECK();
     }
     int h_err = 0;

@@ -444,7 +444,13 @@ static int launch_pass(Source src, KeyT *kout, uint32_t *vout, int64_t n, const 
         BWTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<KeyT>()));
         attr_set = true;
     }
-    prof::Scope ps(sizeof(KeyT) == 4 ? "onesweep_u32" : "onesweep_u64", 2 * n * (int64_t)(sizeof(KeyT) + 4), st);
+    // algorithmic bytes of the launch: every pair written once; read once from arrays, or -- the generator
+    // pass of round 0 -- only the bit-packed text the keys are windows of
+    int64_t read_bytes = n * (int64_t)(sizeof(KeyT) + 4);
+    if constexpr (std::is_same<Source, PackedSuffixSource>::value) read_bytes = packed_hist_bytes(n, src.bits);
+    prof::Scope ps(sizeof(KeyT) == 4 ? (std::is_same<Source, PackedSuffixSource>::value ? "onesweep_u32_gen" : "onesweep_u32")
+                                     : "onesweep_u64",
+                   read_bytes + n * (int64_t)(sizeof(KeyT) + 4), st);
     kern<<<(unsigned)tiles, THREADS, onesweep_smem<KeyT>(), st>>>(
         src, kout, vout, n, d_n, plan.shift[p], plan.bits[p], ws.ghist + p * RADIX,
         ws.status + (int64_t)p * ws.max_tiles * RADIX, ws.counters + p, ws.err);

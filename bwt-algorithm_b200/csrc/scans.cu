@@ -16,6 +16,7 @@
 // reference's adaptive position_step sampling exactly).
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "tma.cuh"
 
 namespace bwtk {
 
@@ -118,18 +119,31 @@ __global__ void __launch_bounds__(THREADS)
     if (ub > u_hi) ub = u_hi;
     if (ua > ub) return;
     const int span = TP + (int)ub + 8;
-    for (int i = threadIdx.x * 4; i < span; i += THREADS * 4) {
+    // The tile (+ halo of the longest unit) arrives as ONE 1-D bulk copy through the TMA unit: no byte
+    // loads, no registers, one elected thread.  Only what the copy cannot carry -- the last < 16 bytes
+    // and the zero padding past the end of the text -- is written by ordinary stores.
+    __shared__ __align__(8) uint64_t s_bar;
+    int bulk = 0;
+    if ((((uintptr_t)(text + t0)) & 15) == 0) {
+        const int64_t avail = n - t0;
+        bulk = (int)((span < avail ? (int64_t)span : avail) & ~15ll);
+    }
+    if (bulk > 0) {
+        if (threadIdx.x == 0) tma::mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma::expect_tx(&s_bar, (uint32_t)bulk);
+            tma::bulk_load(s_text, text + t0, (uint32_t)bulk, &s_bar);
+        }
+    }
+    for (int i = bulk + threadIdx.x * 4; i < span; i += THREADS * 4) {
         uint32_t w = 0;
         int64_t g = t0 + i;
-        if (g + 3 < n) {
-            w = (uint32_t)__ldg(text + g) | ((uint32_t)__ldg(text + g + 1) << 8) |
-                ((uint32_t)__ldg(text + g + 2) << 16) | ((uint32_t)__ldg(text + g + 3) << 24);
-        } else {
-            for (int q = 0; q < 4; q++)
-                if (g + q < n) w |= (uint32_t)__ldg(text + g + q) << (8 * q);
-        }
+        for (int q = 0; q < 4; q++)
+            if (g + q < n) w |= (uint32_t)__ldg(text + g + q) << (8 * q);
         *reinterpret_cast<uint32_t *>(s_text + i) = w;
     }
+    if (bulk > 0) tma::wait(&s_bar, 0);
     __syncthreads();
     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s_text);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

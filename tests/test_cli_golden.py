@@ -90,3 +90,40 @@ def test_reference_unit_tests_on_gpu():
     assert len(by["test12_LONG_IMPERFECT_indel"]) == 1
     r12 = by["test12_LONG_IMPERFECT_indel"][0]
     assert r12.variations and any(v.startswith("9:10:del(") for v in r12.variations)
+
+
+# ---- BASELINE configs[1]: the 150 kb synthetic contig `synC` ----------------------
+SYNC_FASTA_MD5 = "f1e57a0252738b17088fa3ca6dddedf9"
+SYNC_BED_MD5 = "d984e3dc49b02c179ee785ac12bd9330"      # the reference CLI, --jobs 0 --format bed (565 lines)
+
+
+def _write_sync(path):
+    import hashlib
+
+    from tests.util import gen_contig
+
+    seq = gen_contig(150_000, 42).tobytes().decode()
+    with open(path, "w") as fh:
+        fh.write(">synC\n")
+        for i in range(0, len(seq), 80):
+            fh.write(seq[i:i + 80] + "\n")
+    with open(path, "rb") as fh:
+        assert hashlib.md5(fh.read()).hexdigest() == SYNC_FASTA_MD5, "generator drifted from SURVEY Appendix B"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("jobs", ["0", "-1"])
+def test_cli_synC_bed_md5_on_gpu(tmp_path, capsys, jobs):
+    """`python bwt.py synC.fa --jobs 0 --format bed` == the reference CLI's output, by md5."""
+    import hashlib
+
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200 import bwt
+
+    fa, out = tmp_path / "synC.fa", tmp_path / "synC.bed"
+    _write_sync(fa)
+    bwt.main([str(fa), "-o", str(out), "--jobs", jobs, "--format", "bed"])
+    capsys.readouterr()
+    data = out.read_bytes()
+    assert data.count(b"\n") == 565
+    assert hashlib.md5(data).hexdigest() == SYNC_BED_MD5
