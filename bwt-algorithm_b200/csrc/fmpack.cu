@@ -380,29 +380,63 @@ __global__ void __launch_bounds__(256)
                 }
             }
         }
-        int r0 = 0, r1 = 0;
+        // all eight block loads of the step are issued before the first count: eight independent
+        // requests in flight per lane instead of a chain of eight round trips to L2
+        uint4 v[8];
+        int cnt_in[8];         // symbols of this lane's quarter that lie before the position (g > 0)
+        uint32_t sym[8];
+        unsigned flagged = 0;  // requests whose block holds exception symbols (seen by the g == 0 lanes)
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             const unsigned owner = (lane & ~3u) | (unsigned)(t >> 1);
             const uint32_t msg = __shfl_sync(0xffffffffu, (t & 1) ? msg1 : msg0, owner);
-            int part = 0;
+            v[t] = make_uint4(0u, 0u, 0u, 0u);
+            cnt_in[t] = -1;
+            sym[t] = msg >> 30;
             if (msg != 0xffffffffu) {
-                const uint32_t pos = msg & 0x3fffffffu, s2 = msg >> 30;
+                const uint32_t pos = msg & 0x3fffffffu;
                 const uint32_t blk = pos / BLK;
                 const int off = (int)(pos - blk * BLK);
-                if (g == 0 || off > 64 * ((int)g - 1)) {
-                    const uint4 v = __ldg(ix.blocks + (size_t)blk * 4 + g);
-                    if (g == 0) {
-                        part = (int)(s2 == 0 ? (v.x & 0x3fffffffu) : s2 == 1 ? v.y : s2 == 2 ? v.z : v.w);
-                        if (s2 == 0 && (v.x >> 31) && off > 0) part -= exceptions_in(ix, blk * BLK, pos);
-                    } else {
-                        part = count_vec(v, 0x55555555u * s2, off - 64 * ((int)g - 1));
-                    }
+                const int mine = g == 0 ? 0 : off - 64 * ((int)g - 1);
+                if (g == 0 || mine > 0) {
+                    v[t] = __ldg(ix.blocks + (size_t)blk * 4 + g);
+                    cnt_in[t] = mine;
+                }
+            }
+        }
+        int r0 = 0, r1 = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const unsigned owner = (lane & ~3u) | (unsigned)(t >> 1);
+            int part = 0;
+            bool fl = false;
+            if (cnt_in[t] >= 0) {
+                if (g == 0) {
+                    const uint32_t s2 = sym[t];
+                    part = (int)(s2 == 0 ? (v[t].x & 0x3fffffffu) : s2 == 1 ? v[t].y : s2 == 2 ? v[t].z : v[t].w);
+                    fl = s2 == 0 && (v[t].x >> 31);
+                } else {
+                    part = count_vec(v[t], 0x55555555u * sym[t], cnt_in[t]);
                 }
             }
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (lane == owner) { if (t & 1) r1 = part; else r0 = part; }
+            const unsigned fb = __ballot_sync(0xffffffffu, fl);
+            if (lane == owner) {
+                if (t & 1) r1 = part; else r0 = part;
+                if ((fb >> (lane & ~3u)) & 1u) flagged |= 1u << (t & 1);
+            }
+        }
+        if (flagged) {
+            // '$' / N / IUPAC stored as code 0 inside the block: take them out of the A count (rare)
+            if (flagged & 1u) {
+                const uint32_t pos = msg0 & 0x3fffffffu;
+                if (pos % BLK) r0 -= exceptions_in(ix, pos - pos % BLK, pos);
+            }
+            if (flagged & 2u) {
+                const uint32_t pos = msg1 & 0x3fffffffu;
+                if (pos % BLK) r1 -= exceptions_in(ix, pos - pos % BLK, pos);
+            }
         }
         if (c2 >= 0) {
             sp = ix.C4[c2] + r0;

@@ -252,6 +252,21 @@ def cases():
     cs.append(("a14_k7_aliased", rnd(30) + "AAGGCTC" * 9 + rnd(25) + "AAGGCTC" * 3 + "AAGACTC" + "AAGGCTC" * 4 + rnd(20), 3))
     cs.append(("a14_mixed", rnd(50) + "AAAAAAACACACACACACACAC" + rnd(20) + "AAAAAAACAAAAAAAC" + "CAGCAGCAGCAACAGCAGCAGCAG"
                + rnd(30) + "TTGACCGTA" * 6 + "TTGACTGTA" + "TTGACCGTA" * 3 + rnd(40), 3))
+    # Found by probing the reference (texts with planted arrays; the ones kept are those whose reference output is
+    # non-empty): nine more seeded seed-and-extend (a14) cases with one short_imperfect record each, and three
+    # LCP-plateau (a15) cases with period-20 arrays (21, 64 and 30 plateau records).
+    cs.append(("a14x_k7_AAGGCTC_transition", "TTGTCAATAATCTACCGCAAATAAGAGGAAAGGCTCAAGGCTCAAGGCTCAAGGCTCAAGGCTCAAGGCTCAAGGTTCAAGGCTCAAGGCTCCCATAAGTCAAATGTGATCCCGGTTTGT", 3))
+    cs.append(("a14x_k7_AGATTCA_transition", "TAAATCAGTAAGTGTGCGGCTTGACCGCCGTAATTTTCGCAGATTCAAGATTCAAGATTCAAGATTCAAGACTCAAGATTCAAGATTCAAGATTCACACATAGTTTCTTCGACTTGTGAAACGCGGAGGCGC", 3))
+    cs.append(("a14x_k7_ATTGCCA_pure", "ATTATAGCCCTTTGGCACCGTGCGTTCTACCGACCGATGTTTACCATTGCCAATTGCCAATTGCCAATTGCCAATTGCCAATTGCCAATTGCCAATTGCCAATTGCCAATTGCCATTTGCGGCGGTAGATGGAGTAGCAACCATAATTGTGTAGCATAACGCAT", 3))
+    cs.append(("a14x_k8_AACCGGTA_transition", "TTAAATGTTAGGAAGCAGTGATAATCCCGACCCAACCGGTAAACCGGTAGACCGGTAAACCGGTAAACCGGTAAACCGGTAAACCGGTAAACCGGTAGCTATTGTTTGGCCAAGTGGCCAGGCCTGCGA", 3))
+    cs.append(("a14x_k8_ACGGTCAT_pure", "GTTGGTATGTTACCTGCACTAGGCCGGATGCTATCCGGCCTAACGGTCATACGGTCATACGGTCATACGGTCATACGGTCATACGGTCATACGGTCATACGGTCATGCCGAGTTCAACCCTTAGACCCCTCACCAAGTTGATG", 3))
+    cs.append(("a14x_k8_AGGATCCA_transition", "TAATAGTGTATGAATATGGCGTCGCTCCTCTCTGTATAGGATCCAAGGATCCAAGGATCCAAGGATCCAAGGATCCAAGGATCCAAGGGTCCAAGGATCCAAGGATCCACCCTCAACCGAAGCACGGCTGTCGCCAAGGGCGGAACTGCGTAA", 3))
+    cs.append(("a14x_k8_AAGCTTGC_transition", "TCATCACAGATAAGCTCCGGTCGAAGACCGTGAAGCTTGCAAGCTTGCAAGCTTGCAAGCTTGCAAGCTTGCAAACTTGCAAGCTTGCAAGCTTGCAAGCTTGCAAGCTTGCCTATGGGGAGGCCGAGCCCTATCCGGGAGGCTTGCCACTCTCG", 3))
+    cs.append(("a14x_k9_GATTACAGG_pure", "GGGCTTACCCGCTATATACAAACCTGTATGATAAACCAACTTTGCGATTACAGGGATTACAGGGATTACAGGGATTACAGGGATTACAGGGATTACAGGGATTACAGGGATTACAGGGATTACAGGCGGTAAAAGGGCGGTACGGTCGAGCAACTTGAAGAGCCGAGGTGGTG", 3))
+    cs.append(("a14x_k9_AACGGTCAT_pure", "GATATTTGCCAATCGCCCACCAATACATGTTTTGTTGCACATCAGAAACGGTCATAACGGTCATAACGGTCATAACGGTCATAACGGTCATAACGGTCATTGAATTTGGAAAGTGCCGGGCGTGACTCCACCATACTAGATAGTGTG", 3))
+    cs.append(("plat_p20_x5", "AGGGCCATATAAAGTTTGCGCAGCAAGGTCCAAGCTTGCAGACGAATACCTGATTTACACTGTGTGGTAGTTTGCATGCTTGTGTGGTAGTTTGCATGCTTGTGTGGTAGTTTGCATGCTTGTGTGGTAGTTTGCATGCTTGTGTGGTAGTTTGCATGCTACCGGAACGGGTTGCTAAGGGTTGTCGCTTAGTCCTAGTGGCATACCGAACTTCGGTCAA", 1))
+    cs.append(("plat_p20_two", "GACGGGCCGATTAGCAGGCGCGAAAACACGACGAAGCCACGTGCCTACGCCTCCCGTGAGGTGCCTACGCCTCCCGTGAGGTGCCTACGCCTCCCGTGAGGTGCCTACGCCTCCCGTGAGGTTCTTGTACAGGTCCCTTGAGGATTCCTCATTACTCACGCAGCTATCAGAGGCGTCAACCCGGGCCCCTTAGTAGACAAACCGGACCGATAGTAGACAAACCGGACCGATAGTAGACAAACCGGACCGATAGTAGACAAACCGGACCGATAGTAGACAAACCGGACCGATAGTAGACAAACCGGACCGATAGTAGACAAACCGGACCGAGACTTTGCTTATGCTAGGCTCGCTACCACT", 1))
+    cs.append(("plat_p20_mut", "CTAGCAAGTTGGAGGTGCATTGATGGTAATCCGGCATGATCTACGGTCCCACCAGGCGTATGCCTCTTAGACCAGGCGTATGCCTCTTAGACCAGGCGTATGCCTCTTAGACCAGGCGTAAGCCTCTTAGACCAGGCGTATGCCTCTTAGACCAGGCGTATGCCTCTTAGACCAGGCGTATGCCTCTTAGACCAGGCGTATGCCTCTTAGTCTATGAAAACGAGACATCGGAAAATGATTTCCCATGCCGAACGTACGAG", 1))
     cs.append(("adv_empty", "", 0))
     cs.append(("adv_one", "G", 0))
     return cs

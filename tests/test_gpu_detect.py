@@ -191,3 +191,31 @@ def test_pinned_row_pool_reuses_any_large_enough_block(detect):
     # the public path goes through the module's pool
     rows = detect._rows_to_host(torch, big)
     assert np.array_equal(rows, big.cpu().numpy())
+
+
+# ---- n-dependent regimes (bwt.py:1441-1447 Tier 1 position_step; 2193-2228 period scan max_p / step clamps) ----
+def _boundary_sizes():
+    out = []
+    for thr in (10_000, 100_000, 1_000_000, 5_000_000, 10_000_000):
+        out += [thr - 1, thr, thr + 1, thr + 2]      # the text's n with and without '$' lands on both sides
+    return out
+
+
+@pytest.mark.parametrize("n", _boundary_sizes())
+def test_tier1_and_period_scan_at_regime_boundaries(detect, oracle, n):
+    """Just below / at / above every n threshold of the reference, with the sentinel (n + 1 symbols) and without."""
+    body = gen_contig(n, 1000 + n % 977)
+    for text in (body.tobytes() + b"$", body.tobytes()):
+        want = oracle.tier1_scan(text)
+        got, seen = detect.tier1_rows(text, want_seen=True)
+        assert np.array_equal(got, want), f"n={len(text)}: tier 1 rows differ"
+        want_p, want_it = oracle.period_scan(text)
+        got_p, got_it = detect.period_scan_rows(text)
+        assert got_it == want_it and np.array_equal(got_p, want_p), f"n={len(text)}: period scan differs"
+        mask = np.zeros(len(text), np.uint8)
+        for a, b in want[:, :2].tolist():
+            mask[a:b] = 1
+        m = mask[: len(text.rstrip(b"$"))]
+        want_m, it_m = oracle.period_scan(text, tier1_mask=m)
+        got_m, git_m = detect.period_scan_rows(text, tier1_mask=m)
+        assert git_m == it_m and np.array_equal(got_m, want_m), f"n={len(text)}: masked period scan differs"

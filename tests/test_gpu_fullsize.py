@@ -229,6 +229,45 @@ def test_chr21_strict_rows_verify_against_text(torch, chr21):
     assert np.array_equal(pre[pre[:, 1] < lim], rows[rows[:, 1] < lim])
 
 
+def _oracle_strict_window(args):
+    from oracle import oracle as orc
+
+    window, = args
+    return orc.strict_scan(window, 1, 1000, 0, 3)
+
+
+def test_chr21_strict_rows_equal_oracle_on_32_windows(torch, chr21, oracle):
+    """K = 32 windows of 20 kb cut at seeded offsets from the chr21-sized contig, each scanned as a
+    standalone contig by the oracle (all host cores) and by the CUDA path -- and the whole-contig rows that lie
+    strictly inside a window, away from its cuts, must be the window's rows (the scan is a left-to-right greedy
+    per unit length, so a row depends only on the text from its unit's previous emission onwards)."""
+    import multiprocessing as mp
+    import os
+
+    from bwt_algorithm_b200 import detect
+
+    text, ix = chr21
+    W, K = 20_000, 32
+    offs = np.sort(np.random.default_rng(2021).integers(0, CHR21 - W, K))
+    windows = [text[o:o + W].tobytes() + b"$" for o in offs]
+    with mp.get_context("fork").Pool(min(K, os.cpu_count() or 1)) as pool:
+        want = pool.map(_oracle_strict_window, [(w,) for w in windows])
+    whole = detect.strict_rows(ix.text, 1, 1000, 0, 3)
+    n_rows = 0
+    for o, w, exp in zip(offs, windows, want):
+        got = detect.strict_rows(w, 1, 1000, 0, 3)
+        assert np.array_equal(got, exp), f"window at {o}: strict rows differ from the oracle"
+        n_rows += len(exp)
+        # rows of the whole-contig scan well inside the window == the window's rows there (shifted)
+        lo, hi = o + 3000, o + W - 3000
+        inside = whole[(whole[:, 0] >= lo) & (whole[:, 1] <= hi)].copy()
+        inside[:, 0] -= o
+        inside[:, 1] -= o
+        sub = exp[(exp[:, 0] >= 3000) & (exp[:, 1] <= W - 3000)]
+        assert np.array_equal(inside, sub), f"window at {o}: whole-contig rows differ inside the window"
+    assert n_rows > 20_000
+
+
 def test_chr1_sized_contig_index_and_search(torch):
     """configs[3]: all 1-10 bp motifs on a chr1-sized contig."""
     from bwt_algorithm_b200.device_index import DeviceIndex

@@ -14,11 +14,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SHORT = [("onesweep_kernel<unsigned int, bwtk::rsort::PackedSuffixSource", "onesweep_u32_gen"),
+         ("onesweep_kernel<unsigned int, rsort::PackedSuffixSource", "onesweep_u32_gen"),
+         ("onesweep_kernel<unsigned int, PackedSuffixSource", "onesweep_u32_gen"),
          ("onesweep_kernel<unsigned int", "onesweep_u32"), ("onesweep_kernel<unsigned long", "onesweep_u64"),
          ("regroup_kernel<unsigned int", "regroup_first"), ("regroup_kernel<unsigned long", "regroup_round"),
          ("hist_kernel<unsigned long", "radix_hist_u64"), ("hist_kernel<unsigned int", "radix_hist_u32"),
-         ("fmp::search_coop_kernel", "fm_search_coop_kernel"), ("fmp::search_kernel", "fm_search_thread_kernel"),
-         ("fmp::sweep_level_kernel", "fm_sweep_level_kernel"), ("fm::bsearch_kernel", "bsearch_kernel_byte_bwt")]
+         ("search_coop_kernel", "fm_search_coop_kernel"), ("search_kernel", "fm_search_thread_kernel"),
+         ("bsearch_kernel", "bsearch_kernel_byte_bwt")]
 
 
 def short_name(full):
@@ -45,7 +47,7 @@ def read_csv(path):
 def summarise(launches):
     per = {}
     for r in launches:
-        if "bwtk" not in r["name"]:
+        if "at::" in r["name"] or "elementwise" in r["name"]:
             continue                       # torch's own kernels (fills, copies) are not part of the step
         k = per.setdefault(short_name(r["name"]), {"launches": 0, "ns": 0.0, "dram_read": 0.0, "dram_write": 0.0,
                                                   "lts_sectors": 0.0, "hit_w": 0.0})
