@@ -47,6 +47,8 @@ _SIGS = {
     "bwtk_profile_report": (_i32, [C.c_char_p, _i32]),
     "bwtk_upload_text": (_i32, [_p, _p, _i64, _p]),
     "bwtk_download": (_i32, [_p, _p, _i64, _p]),
+    "bwtk_fasta_index": (_i32, [_p, _i64, _p, _i64, _p, _p]),
+    "bwtk_fasta_sequence": (_i64, [_p, _i64, _i64, _i64, _i64, _i32, _p]),
     "bwtk_byte_histogram": (_i32, [_p, _i64, _p, _p]),
     "bwtk_sa_workspace_bytes": (_i64, [_i64]),
     "bwtk_sa_build": (_i32, [_p, _i64, _p, _p, _p, _i64, _p, _p]),

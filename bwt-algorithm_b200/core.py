@@ -82,15 +82,25 @@ class BWTCore:
     BITS_TO_BASE = {0: "A", 1: "C", 2: "G", 3: "T"}
 
     def __init__(self, text: str, sa_sample_rate: int = 32, occ_sample_rate: int = 128, device=None,
-                 _index: DeviceIndex = None):
+                 _index: DeviceIndex = None, _pinned_text=None):
         self.text: str = text
         self.n = len(text)
         self.sa_sample_rate = sa_sample_rate
         self.occ_sample_rate = occ_sample_rate
-        raw = text.encode("utf-8")
-        self._host: Dict[str, object] = {"text_arr": np.frombuffer(raw, dtype=np.uint8)}
-        # one H2D copy of the text, then everything is built in HBM
-        self._dev = _index if _index is not None else DeviceIndex(raw, occ_rate=int(occ_sample_rate), device=device)
+        if _pinned_text is not None and _index is None and int(_pinned_text.numel()) == len(text):
+            # the FASTA parser already wrote these bytes into pinned host memory: upload from there
+            self._host: Dict[str, object] = {"text_arr": _pinned_text.numpy()}
+            import torch
+
+            dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+            self._dev = DeviceIndex(_pinned_text.to(dev, non_blocking=True), occ_rate=int(occ_sample_rate),
+                                    device=dev, text_is_device=True)
+        else:
+            raw = text.encode("utf-8")
+            self._host = {"text_arr": np.frombuffer(raw, dtype=np.uint8)}
+            # one H2D copy of the text, then everything is built in HBM
+            self._dev = _index if _index is not None else DeviceIndex(raw, occ_rate=int(occ_sample_rate),
+                                                                      device=device)
         self.alphabet = sorted(set(text))
         self.char_to_code = {c: ord(c) for c in self.alphabet}
         self.code_to_char = {ord(c): c for c in self.alphabet}

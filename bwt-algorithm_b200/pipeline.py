@@ -38,7 +38,10 @@ def _process_chromosome_worker(args):
     perfection filter (bwt.py:3040-3141).  Exceptions are reported and yield []."""
     chrom, seq, config = args
     try:
-        core = BWTCore(seq + "$", config["sa_sample_rate"])
+        pinned = _PINNED.get(chrom)
+        if pinned is not None and pinned.numel() != len(seq) + 1:
+            pinned = None                      # a different contig of the same name
+        core = BWTCore(seq + "$", config["sa_sample_rate"], _pinned_text=pinned)
         found: List[TandemRepeat] = []
         verbose = config.get("show_progress", False)
         if verbose:
@@ -109,6 +112,21 @@ def _process_and_finish_contig(args):
         return [], len(raw), len(raw), len(raw)
 
 
+# Pinned host copies (trimmed text + '$') of the contigs of the FASTA loaded last, filled by the native
+# parser; the in-process worker uploads from here.  Worker processes (one per GPU) do not see it and
+# encode their contig as before.
+_PINNED: Dict[str, object] = {}
+
+
+def _pinning_enabled() -> bool:
+    try:
+        import torch
+
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False
+
+
 class _LazyCores(dict):
     """``bwt_cores`` of the CLI path: chrom -> BWTCore, each built on first access."""
 
@@ -176,7 +194,20 @@ class TandemRepeatFinder:
         sequences[name] = trimmed
 
     def load_reference(self) -> Dict[str, str]:
-        """FASTA -> {name: upper-cased, flank-trimmed sequence} (bwt.py:3713-3756)."""
+        """FASTA -> {name: upper-cased, flank-trimmed sequence} (bwt.py:3713-3756).
+
+        ASCII files are parsed natively (csrc/fasta.cu: one index pass, then every record's sequence is
+        written upper-cased straight into its buffer -- and, when a GPU is present, the trimmed text with
+        its '$' into PINNED host memory, from where the per-contig worker uploads it without another
+        copy).  Anything else (non-ASCII bytes, a header without a name) goes through the reference's own
+        line loop, which defines the behaviour."""
+        sequences = self._load_reference_native()
+        if sequences is None:
+            sequences = self._load_reference_lines()
+        self.sequences = sequences
+        return sequences
+
+    def _load_reference_lines(self) -> Dict[str, str]:
         sequences: Dict[str, str] = {}
         name, chunks = None, []
         with open(self.reference_file, "r") as fh:
@@ -190,7 +221,55 @@ class TandemRepeatFinder:
                     chunks.append(line.upper())
         if name:
             self._register(sequences, name, chunks)
-        self.sequences = sequences
+        return sequences
+
+    def _load_reference_native(self) -> Optional[Dict[str, str]]:
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib
+
+        try:
+            L = _lib.lib()
+        except _lib.BwtkError:
+            return None
+        data = np.fromfile(self.reference_file, dtype=np.uint8)
+        if data.size == 0:
+            return {}
+        cap = 1024
+        while True:
+            rec = np.zeros((cap, 5), np.int64)
+            count, flags = C.c_int64(0), C.c_int32(0)
+            rc = L.bwtk_fasta_index(data.ctypes.data, data.size, rec.ctypes.data, cap, C.addressof(count),
+                                    C.addressof(flags))
+            if rc == _lib.E_OVERFLOW:
+                cap = int(count.value)
+                continue
+            break
+        if rc != 0 or (flags.value & 1):
+            return None
+        pin = _PINNED if _pinning_enabled() else None
+        if pin is not None:
+            pin.clear()
+        sequences: Dict[str, str] = {}
+        for name_off, name_len, body_off, body_end, seq_len in rec[: count.value].tolist():
+            name = data[name_off:name_off + name_len].tobytes().decode("ascii")
+            buf = np.empty(seq_len, np.uint8)
+            if L.bwtk_fasta_sequence(data.ctypes.data, body_off, body_end, 0, seq_len, 0, buf.ctypes.data) != seq_len:
+                return None
+            full = buf.tobytes().decode("ascii")
+            self.full_sequences[name] = full
+            left = 0 if seq_len <= 2 * self.flank_trim else self.flank_trim
+            keep = seq_len - 2 * left
+            self.trim_offsets[name] = left
+            sequences[name] = full[left:left + keep] if left else full
+            if pin is not None and keep > 0:
+                import torch
+
+                t = torch.empty(keep + 1, dtype=torch.uint8, pin_memory=True)
+                if L.bwtk_fasta_sequence(data.ctypes.data, body_off, body_end, left, keep, 1, t.data_ptr()) == keep + 1:
+                    pin[name] = t
         return sequences
 
     def build_indices(self, sequences: Dict[str, str], lazy: bool = False):

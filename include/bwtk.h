@@ -64,6 +64,19 @@ int32_t bwtk_upload_text(const uint8_t *h_pinned, uint8_t *d_dst, int64_t n, voi
  * over PCIe, for the same reason.  Both pointers 16-byte aligned.  Asynchronous. */
 int32_t bwtk_download(const void *d_src, void *h_pinned, int64_t bytes, void *stream);
 
+/* ---- FASTA ingest: TandemRepeatFinder.load_reference (bwt.py:3713-3756), host code -----
+ * Two passes over the file's bytes with the reference's line rules (strip, '>' headers, first
+ * token = name, upper-case, lines before the first header dropped; line ends \n, \r\n, \r).
+ * bwtk_fasta_index: h_rec[count][5] = name_off, name_len, body_off, body_end, seq_len;
+ * BWTK_EOVERFLOW with the record count when cap is too small; BWTK_EINVAL for a header without
+ * a name; *h_flags bit 0 = non-ASCII bytes present (caller must use the reference's own loop).
+ * bwtk_fasta_sequence: symbols [skip, skip+take) of one record, upper-cased, into dst (e.g.
+ * pinned host memory), '$' appended when sentinel != 0; returns bytes written or < 0. */
+int32_t bwtk_fasta_index(const uint8_t *buf, int64_t len, int64_t *h_rec, int64_t cap, int64_t *h_count,
+                         int32_t *h_flags);
+int64_t bwtk_fasta_sequence(const uint8_t *buf, int64_t body_off, int64_t body_end, int64_t skip,
+                            int64_t take, int32_t sentinel, uint8_t *dst);
+
 /* ---- a5: BWTCore._build_char_counts (bwt.py:276-286) ------------------
  * byte histogram of the text; h_totals[256] (host) receives the counts.
  * The exclusive prefix sum over present bytes (the FM "C" array) is a 256-entry

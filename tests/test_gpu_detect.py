@@ -216,6 +216,8 @@ def test_tier1_and_period_scan_at_regime_boundaries(detect, oracle, n):
         for a, b in want[:, :2].tolist():
             mask[a:b] = 1
         m = mask[: len(text.rstrip(b"$"))]
+        # the kernel's seen mask is the union of the Tier 1 calls: what GenomeScanner hands to the period scan
+        assert np.array_equal(seen[: m.size] != 0, m != 0), f"n={len(text)}: seen mask != union of the Tier 1 rows"
         want_m, it_m = oracle.period_scan(text, tier1_mask=m)
         got_m, git_m = detect.period_scan_rows(text, tier1_mask=m)
         assert git_m == it_m and np.array_equal(got_m, want_m), f"n={len(text)}: masked period scan differs"
