@@ -56,44 +56,53 @@ def tier1_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str) -> Li
     return out
 
 
-def strict_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str, max_mismatch: int) -> List[TandemRepeat]:
-    """Rows (start,end,primitive_period,copies) -> strict-scan records (bwt.py:1951-1996)."""
-    out: List[TandemRepeat] = []
+class StrictRecordMaker:
+    """(start, end, primitive period, copies) -> the record ``find_long_unit_repeats_strict`` builds for
+    an exact array (bwt.py:1951-1996).  ``MotifUtils.calculate_trf_statistics(text_arr, start, end, motif,
+    count, 0.0)`` is unrolled with its per-motif parts (composition, entropy) computed once per distinct
+    motif and its mismatch-free arithmetic written out: a chr21-sized contig yields millions of calls."""
+
+    def __init__(self, text_arr: np.ndarray, chromosome: str, max_mismatch: int, text_bytes: Optional[bytes] = None):
+        self.text = text_bytes if text_bytes is not None else text_arr.tobytes()
+        self.size = len(self.text)
+        self.chromosome = chromosome
+        self.per_motif: Dict[bytes, tuple] = {}
+        self.pm = (1.0 - 0.0) * 100.0
+        self.mm_per_copy = 0 if self.pm >= 99.9 else max_mismatch
+
+    def __call__(self, start: int, end: int, prim: int, count: int) -> TandemRepeat:
+        text = self.text
+        raw = text[start:start + prim]
+        known = self.per_motif.get(raw)
+        if known is None:
+            motif = raw.decode("ascii", errors="replace")
+            known = self.per_motif[raw] = (motif, MotifUtils.calculate_composition(motif),
+                                           MotifUtils.calculate_entropy(motif))
+        motif, comp, ent = known
+        length = end - start
+        actual = text[start:end].decode("ascii", errors="replace") if end <= self.size else motif * int(count)
+        score = max(0, int((length * (1.0 - 0.0) * 2) - (length * 0.0 * 7)))
+        # positional, in the field order of records.TandemRepeat (bwt.py:429-452)
+        return TandemRepeat(self.chromosome, start, end, motif, float(count), length, 2, 0.95, motif, 0.0,
+                            self.mm_per_copy, count, "+", self.pm, 0.0, score, dict(comp), ent, actual, None)
+
+
+def strict_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str, max_mismatch: int,
+                   text_bytes: Optional[bytes] = None) -> List[TandemRepeat]:
+    """Rows (start,end,primitive_period,copies) -> strict-scan records (bwt.py:1951-1996).
+    `text_bytes`: the bytes of `text_arr` when the caller already holds them."""
     if len(rows) == 0:
-        return out
-    # A chr21-sized contig yields millions of short exact arrays, so this loop is the CLI's
-    # real bottleneck: MotifUtils.calculate_trf_statistics(text_arr, start, end, motif, count, 0.0)
-    # is unrolled here with its per-motif parts (composition, entropy) computed once per
-    # distinct motif and its mismatch-free arithmetic written out.
-    text = text_arr.tobytes()
-    size = len(text)
-    per_motif = {}
-    pm = (1.0 - 0.0) * 100.0
-    mm_per_copy = 0 if pm >= 99.9 else max_mismatch
-    append = out.append
+        return []
+    make = StrictRecordMaker(text_arr, chromosome, max_mismatch, text_bytes)
     # millions of records, each owning a dict: the cyclic collector would rescan the growing list
     # again and again (it more than doubles the loop's time), and nothing here can form a cycle
     gc_was_on = gc.isenabled()
     gc.disable()
     try:
-        for start, end, prim, count in rows[:, :4].tolist():
-            raw = text[start:start + prim]
-            known = per_motif.get(raw)
-            if known is None:
-                motif = raw.decode("ascii", errors="replace")
-                known = per_motif[raw] = (motif, MotifUtils.calculate_composition(motif),
-                                          MotifUtils.calculate_entropy(motif))
-            motif, comp, ent = known
-            length = end - start
-            actual = text[start:end].decode("ascii", errors="replace") if end <= size else motif * int(count)
-            score = max(0, int((length * (1.0 - 0.0) * 2) - (length * 0.0 * 7)))
-            # positional, in the field order of records.TandemRepeat (bwt.py:429-452)
-            append(TandemRepeat(chromosome, start, end, motif, float(count), length, 2, 0.95, motif, 0.0,
-                                mm_per_copy, count, "+", pm, 0.0, score, dict(comp), ent, actual, None))
+        return [make(start, end, prim, count) for start, end, prim, count in rows[:, :4].tolist()]
     finally:
         if gc_was_on:
             gc.enable()
-    return out
 
 
 def plateau_records(text_arr: np.ndarray, rows: np.ndarray, chromosome: str) -> List[TandemRepeat]:

@@ -134,7 +134,18 @@ class MotifUtils:
         Tie order substitution > deletion > insertion (strict <); the end column
         is the first minimum in [m-max_indel, m+max_indel]; rejected when
         substitutions exceed the tolerance or an indel total exceeds max_indel.
+
+        A pure function of its arguments; short motifs (the merge stage asks about the same few
+        homopolymer / dinucleotide windows hundreds of thousands of times per contig) are memoised.
+        The result is shared between callers and must not be mutated.
         """
+        if len(motif) <= 12:
+            return _align_unit_cached(motif, window, max_indel, mismatch_tolerance)
+        return MotifUtils._align_unit_to_window_dp(motif, window, max_indel, mismatch_tolerance)
+
+    @staticmethod
+    def _align_unit_to_window_dp(motif: str, window: str, max_indel: int,
+                                 mismatch_tolerance: int) -> Optional[AlignmentResult]:
         m, n = len(motif), len(window)
         if m == 0 or n == 0:
             return None
@@ -465,3 +476,8 @@ class MotifUtils:
                 yield from grow(prefix + ch)
 
         yield from grow("")
+
+
+@functools.lru_cache(maxsize=1 << 17)
+def _align_unit_cached(motif: str, window: str, max_indel: int, mismatch_tolerance: int):
+    return MotifUtils._align_unit_to_window_dp(motif, window, max_indel, mismatch_tolerance)

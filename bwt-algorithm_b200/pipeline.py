@@ -33,42 +33,55 @@ def _elapsed(t0: float) -> str:
     return f"{int(e // 60)}m {int(e % 60)}s" if e >= 60 else f"{int(e)}s"
 
 
-def _process_chromosome_worker(args):
-    """One contig: index build + strict adjacency scan + the short-motif
-    perfection filter (bwt.py:3040-3141).  Exceptions are reported and yield []."""
-    chrom, seq, config = args
+def _detect_rows(chrom: str, seq: str, config: dict):
+    """One contig at row level: index build + strict adjacency scan (bwt.py:3040-3106).  Returns
+    (rows int32[R, 8] or None when no detector ran, text_arr uint8 incl. '$', max_mismatch)."""
+    import numpy as np
+
+    from . import detect
+    from .finders import _device_text_of
+
+    pinned = _PINNED.get(chrom)
+    if pinned is not None and pinned.numel() != len(seq) + 1:
+        pinned = None                      # a different contig of the same name
+    core = BWTCore(seq + "$", config["sa_sample_rate"], _pinned_text=pinned)
+    verbose = config.get("show_progress", False)
+    rows = None
     try:
-        pinned = _PINNED.get(chrom)
-        if pinned is not None and pinned.numel() != len(seq) + 1:
-            pinned = None                      # a different contig of the same name
-        core = BWTCore(seq + "$", config["sa_sample_rate"], _pinned_text=pinned)
-        found: List[TandemRepeat] = []
-        verbose = config.get("show_progress", False)
         if verbose:
             print(f"  [{chrom}] Building indices ({len(seq):,} bp)...")
         if config.get("enable_tier2", False):
             if len(seq) > 50_000_000 and not verbose:
                 pass  # very large contigs are skipped unless --progress is given (bwt.py:3070)
             else:
-                tier2 = Tier2LCPFinder(core, min_period=1, max_period=config["max_period"],
-                                       max_short_motif=config["max_motif_length"],
-                                       allow_mismatches=config["allow_mismatches"], show_progress=verbose)
-                tier2.min_copies = config["min_copies"]
-                tier2.min_entropy = config["min_entropy"]
                 min_copies = config["min_copies"]
                 unit_cap = max(config["max_unit_len"], min(len(seq) // min_copies, 1000))
-                strict = tier2.find_long_unit_repeats_strict(chrom, min_unit_len=1, max_unit_len=unit_cap,
-                                                             max_mismatch=0, min_copies=min_copies)
-                found.extend(strict)
+                rows = detect.strict_rows(_device_text_of(core), 1, unit_cap, 0, min_copies)
                 if verbose:
-                    print(f"  [{chrom}] Strict adjacency: {len(strict)} tandem repeats detected")
+                    print(f"  [{chrom}] Strict adjacency: {len(rows)} tandem repeats detected")
+        text_arr = np.array(core.text_arr, copy=True) if rows is not None and len(rows) else None
+    finally:
+        core.clear()
+    return rows, text_arr
+
+
+def _process_chromosome_worker(args):
+    """One contig: index build + strict adjacency scan + the short-motif
+    perfection filter (bwt.py:3040-3141).  Exceptions are reported and yield []."""
+    chrom, seq, config = args
+    try:
+        from .finders import strict_records
+
+        rows, text_arr = _detect_rows(chrom, seq, config)
+        found: List[TandemRepeat] = []
+        if rows is not None and len(rows):
+            found = strict_records(text_arr, rows, chrom, 0)
         kept = []
         for r in found:
             motif = r.consensus_motif or r.motif
             if len(motif) < 5 and r.copies < 30 and (r.mismatch_rate > 0 or r.max_mismatches_per_copy > 0):
                 continue
             kept.append(r)
-        core.clear()
         return kept
     except Exception as exc:  # the reference swallows worker failures the same way
         print(f"ERROR processing chromosome {chrom}: {exc}")
@@ -84,8 +97,12 @@ def _distinct_sort_names(names) -> bool:
 
 
 def _finish_contig(chrom: str, seq: str, config: dict, left: str, right: str, raw: List["TandemRepeat"]):
-    """The post-processing chain of one contig, away from the parent: a finder that knows just this
+    """The post-processing chain of one contig on records, away from the parent: a finder that knows just this
     contig (trimmed sequence for the re-alignments, flanks for the coordinate restore)."""
+    return _contig_finder(chrom, seq, config, left, right)._postprocess_counts(raw)
+
+
+def _contig_finder(chrom: str, seq: str, config: dict, left: str, right: str) -> "TandemRepeatFinder":
     finder = TandemRepeatFinder(
         "", sa_sample_rate=config["sa_sample_rate"], show_progress=config.get("show_progress", False),
         allow_mismatches=config["allow_mismatches"], max_motif_length=config["max_motif_length"],
@@ -94,22 +111,35 @@ def _finish_contig(chrom: str, seq: str, config: dict, left: str, right: str, ra
     finder.sequences = {chrom: seq}
     finder.full_sequences = {chrom: left + seq + right}
     finder.trim_offsets = {chrom: len(left)}
-    return finder._postprocess_counts(raw)
+    return finder
 
 
 def _process_and_finish_contig(args):
-    """Worker of the multi-process path: detection (bwt.py:3040-3141), then this contig's share of the
-    post-processing chain.  Returns (final calls, raw, after suppression, after dedup)."""
+    """Worker of the per-contig path: detection (bwt.py:3040-3141) at row level, then this contig's share of
+    the post-processing chain on the rows (rowchain.finish_rows) -- records are only built for the calls
+    that survive.  Returns (final calls, raw, after suppression, after dedup)."""
     chrom, seq, config, left, right = args
-    raw = _process_chromosome_worker((chrom, seq, config))
     try:
-        return _finish_contig(chrom, seq, config, left, right, raw)
+        rows, text_arr = _detect_rows(chrom, seq, config)
+    except Exception as exc:  # the reference swallows worker failures the same way
+        print(f"ERROR processing chromosome {chrom}: {exc}")
+        import traceback
+
+        traceback.print_exc()
+        return [], 0, 0, 0
+    n_raw = 0 if rows is None else len(rows)
+    if not n_raw:
+        return [], 0, 0, 0
+    try:
+        from . import rowchain
+
+        return rowchain.finish_rows(_contig_finder(chrom, seq, config, left, right), chrom, text_arr, rows)
     except Exception as exc:  # same policy as the detection worker
         print(f"ERROR post-processing chromosome {chrom}: {exc}")
         import traceback
 
         traceback.print_exc()
-        return [], len(raw), len(raw), len(raw)
+        return [], n_raw, n_raw, n_raw
 
 
 # Pinned host copies (trimmed text + '$') of the contigs of the FASTA loaded last, filled by the native
@@ -326,15 +356,33 @@ class TandemRepeatFinder:
         raw: List[TandemRepeat] = []
         items = list(self.sequences.items())
         total = len(items)
+        # Every stage of the chain works inside one contig, so with distinct contig sort keys each contig is
+        # finished at row level right after its scan (rowchain.finish_rows) and the results are sorted once.
+        per_contig = _distinct_sort_names(self.sequences)
+        cfg = self._config(enable_tier1, enable_tier2)
+        finished: List[TandemRepeat] = []
+        n_raw = n_kept = 0
         for idx, (chrom, seq) in enumerate(items, 1):
             pct = (idx - 1) / total * 100 if total else 100.0
             print(f"\n[{_bar(idx - 1, total)}] {pct:.1f}% ({idx}/{total})")
             print(f"Scanning chromosome {chrom} ({len(seq):,} bp)...")
-            got = _process_chromosome_worker((chrom, seq, self._config(enable_tier1, enable_tier2)))
-            raw.extend(got)
-            print(f"  Detected {len(got)} STR blocks")
+            if per_contig:
+                part, a, b, _c = _process_and_finish_contig(self._finish_tasks([(chrom, seq, cfg)])[0])
+                finished.extend(part)
+                n_raw, n_kept = n_raw + a, n_kept + b
+                print(f"  Detected {a} STR blocks")
+            else:
+                got = _process_chromosome_worker((chrom, seq, cfg))
+                raw.extend(got)
+                print(f"  Detected {len(got)} STR blocks")
         print(f"\n[{'█' * _BAR}] 100.0% ({total}/{total})")
-        final, _ = self._postprocess(raw, print)
+        if per_contig:
+            if n_kept < n_raw:
+                print(f"Nested call suppression: {n_raw} -> {n_kept} repeats")
+            finished.sort(key=self._repeat_sort_key)
+            final = finished
+        else:
+            final, _ = self._postprocess(raw, print)
         print(f"Analysis complete! Found {len(final)} total repeats.")
         return final
 
@@ -362,8 +410,7 @@ class TandemRepeatFinder:
         # finishes its contigs itself: the chain runs in parallel and only the final calls (a few percent
         # of the raw ones) are pickled back.  Needs contig names with distinct sort keys, so that sorting
         # the concatenation equals the chain's own sorts of the mixed list.
-        per_contig = (sharding.worker_processes(len(tasks), n_jobs) > 1
-                      and _distinct_sort_names(self.sequences) and not (enable_tier3 and long_reads))
+        per_contig = _distinct_sort_names(self.sequences) and not (enable_tier3 and long_reads)
         if per_contig:
             finished: List[TandemRepeat] = []
             n_raw = n_kept = n_unique = 0

@@ -77,6 +77,14 @@ int32_t bwtk_fasta_index(const uint8_t *buf, int64_t len, int64_t *h_rec, int64_
 int64_t bwtk_fasta_sequence(const uint8_t *buf, int64_t body_off, int64_t body_end, int64_t skip,
                             int64_t take, int32_t sentinel, uint8_t *dst);
 
+/* ---- post-processing on rows: TandemRepeatFinder._suppress_nested_short_calls (bwt.py:3402-3497),
+ * host code.  One entry per call of ONE contig (start, end, len(motif), mismatch_rate > 0);
+ * keep[i] = 1 when the call survives: not overlapped by a KEPT call with a strictly longer motif
+ * for >= 80 % of its length (homopolymers), >= 10 % / 30 % (motif >= 10x / 5x longer) or
+ * >= overlap_threshold otherwise.  Same survivors as the reference's quadratic loop. */
+int32_t bwtk_suppress_nested(const int32_t *start, const int32_t *end, const int32_t *motif_len,
+                             const uint8_t *imperfect, int64_t n, double overlap_threshold, uint8_t *keep);
+
 /* ---- a5: BWTCore._build_char_counts (bwt.py:276-286) ------------------
  * byte histogram of the text; h_totals[256] (host) receives the counts.
  * The exclusive prefix sum over present bytes (the FM "C" array) is a 256-entry

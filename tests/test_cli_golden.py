@@ -48,6 +48,21 @@ def test_host_glue_reproduces_reference_outputs(oracle, tmp_path, fa, flags, tag
             rows = oracle.strict_scan(text, 1, eff, 0, 3)
             raw.extend(finders.strict_records(np.frombuffer(text, np.uint8), rows, chrom, 0))
     final, _dups = finder._postprocess(raw, lambda m: None)
+    # the row-oriented chain per contig (what the CLI runs) yields the same calls
+    import dataclasses
+
+    from bwt_algorithm_b200 import pipeline, rowchain
+
+    by_rows = []
+    if "--tier1" not in flags and pipeline._distinct_sort_names(seqs):
+        cfg = finder._config(True, True)
+        for chrom, seq, c, left, right in finder._finish_tasks([(ch, sq, cfg) for ch, sq in seqs.items()]):
+            text = (seq + "$").encode()
+            rows = oracle.strict_scan(text, 1, max(120, min(len(seq) // 3, 1000)), 0, 3)
+            by_rows.extend(rowchain.finish_rows(pipeline._contig_finder(chrom, seq, c, left, right), chrom,
+                                                np.frombuffer(text, np.uint8), rows)[0])
+        by_rows.sort(key=finder._repeat_sort_key)
+        assert [dataclasses.astuple(r) for r in by_rows] == [dataclasses.astuple(r) for r in final]
     for fmt in FORMATS:
         out = tmp_path / f"{tag}.{fmt}"
         finder.save_results(final, str(out), fmt)

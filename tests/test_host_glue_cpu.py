@@ -225,6 +225,12 @@ def test_postprocessing_chain_equals_reference_golden():
     again, dups = f._postprocess(finders.strict_records(np.frombuffer(seq.encode(), np.uint8), rows, g["chrom"], 0),
                                  lambda msg: None)
     assert digest(again) == g["digest"] and dups == g["stage_counts"][0] - g["stage_counts"][2]
+    # the row-oriented chain (rowchain.finish_rows: records only for what survives) gives the same list
+    from bwt_algorithm_b200 import rowchain
+
+    rfinal, n_raw, n_kept, n_unique = rowchain.finish_rows(f, g["chrom"], np.frombuffer(seq.encode(), np.uint8), rows)
+    assert [n_raw, n_kept, n_unique] == g["stage_counts"][:3]
+    assert digest(rfinal) == g["digest"] and [r.to_bed() for r in rfinal] == g["bed"]
 
 
 def test_per_contig_finish_equals_global_chain(oracle, tmp_path):
@@ -267,35 +273,115 @@ def test_per_contig_finish_equals_global_chain(oracle, tmp_path):
         assert sums == [n_raw, n_kept, n_unique]
         assert [dataclasses.astuple(r) for r in got] == [dataclasses.astuple(r) for r in want]
         assert len(want) > 0
+        # ... and so does the row-oriented chain, which never builds the records that do not survive
+        from bwt_algorithm_b200 import rowchain
+
+        got2, sums2 = [], [0, 0, 0]
+        for chrom, seq, c, left, right in tasks:
+            text = (seq + "$").encode()
+            rows = oracle.strict_scan(text, 1, max(120, min(len(seq) // 3, 1000)), 0, 3)
+            part, a, b, c3 = rowchain.finish_rows(pipeline._contig_finder(chrom, seq, c, left, right), chrom,
+                                                  np.frombuffer(text, np.uint8), rows)
+            got2.extend(part)
+            sums2 = [sums2[0] + a, sums2[1] + b, sums2[2] + c3]
+        got2.sort(key=finder._repeat_sort_key)
+        assert sums2 == [n_raw, n_kept, n_unique]
+        assert [dataclasses.astuple(r) for r in got2] == [dataclasses.astuple(r) for r in want]
     pickle.dumps(pipeline._process_and_finish_contig)                # spawn-able: top level, importable
     assert not pipeline._distinct_sort_names(["chr1", "Chr1"])       # equal sort keys: the global chain is used
 
 
-def test_parallel_driver_per_contig_branch(oracle, monkeypatch, capsys):
-    """find_tandem_repeats_parallel with several worker processes (simulated in-process, detection
-    served by the oracle) returns what the single-process branch returns, with the same summary lines."""
+def test_drivers_use_the_row_chain_and_match_the_object_chain(oracle, monkeypatch, capsys):
+    """find_tandem_repeats / find_tandem_repeats_parallel (detection served by the oracle) finish every contig
+    at row level; the calls and the summary lines are those of the object chain on the mixed list."""
     import dataclasses
     import os
 
     from bwt_algorithm_b200 import pipeline, sharding
 
-    def fake_detection(args):
-        chrom, seq, config = args
+    def fake_rows(chrom, seq, config):
         text = (seq + "$").encode()
         rows = oracle.strict_scan(text, 1, max(config["max_unit_len"], min(len(seq) // config["min_copies"], 1000)),
                                   0, config["min_copies"])
-        return finders.strict_records(np.frombuffer(text, np.uint8), rows, chrom, 0)
+        return rows, np.frombuffer(text, np.uint8)
 
-    monkeypatch.setattr(pipeline, "_process_chromosome_worker", fake_detection)
+    monkeypatch.setattr(pipeline, "_detect_rows", fake_rows)
     fixture = os.path.join(os.path.dirname(__file__), "golden", "cli", "test2.fa")
-    outs = []
+    ref = TandemRepeatFinder(fixture)
+    seqs = ref.load_reference()
+    mixed = []
+    for chrom, seq in seqs.items():
+        rows, text_arr = fake_rows(chrom, seq, ref._config(False, True))
+        mixed.extend(finders.strict_records(text_arr, rows, chrom, 0))
+    want, n_raw, n_kept, n_unique = ref._postprocess_counts(mixed)
+    assert n_kept < n_raw and len(want) > 0
+    want_t = [dataclasses.astuple(r) for r in want]
     for procs in (1, 2):
         monkeypatch.setattr(sharding, "worker_processes", lambda n_tasks, n_jobs, procs=procs: procs)
         monkeypatch.setattr(sharding, "run_tasks", lambda worker, tasks, n_jobs: (worker(t) for t in tasks))
         finder = TandemRepeatFinder(fixture)
         finder.load_reference()
         final = finder.find_tandem_repeats_parallel(enable_tier1=False, enable_tier2=True, n_jobs=4)
-        text = capsys.readouterr().out
-        outs.append(([dataclasses.astuple(r) for r in final],
-                     [ln for ln in text.splitlines() if ln.startswith(("Nested call", "Analysis complete"))]))
-    assert outs[0] == outs[1] and len(outs[0][0]) > 0 and len(outs[0][1]) == 2
+        lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith(("Nested call", "Analysis complete"))]
+        assert [dataclasses.astuple(r) for r in final] == want_t
+        assert lines == [f"Nested call suppression: {n_raw} -> {n_kept} repeats",
+                         f"Analysis complete! Found {len(want)} unique repeats"
+                         + (f" (deduplicated {n_raw - n_unique})." if n_raw - n_unique > 0 else ".")]
+    finder = TandemRepeatFinder(fixture)
+    finder.load_reference()
+    final = finder.find_tandem_repeats(enable_tier1=False, enable_tier2=True)
+    out = capsys.readouterr().out
+    assert [dataclasses.astuple(r) for r in final] == want_t
+    assert f"Nested call suppression: {n_raw} -> {n_kept} repeats" in out
+    assert f"Analysis complete! Found {len(want)} total repeats." in out
+    # the worker of the reference API still returns records (bwt.py:3040-3141)
+    recs = pipeline._process_chromosome_worker(("c", "ACGT" * 3 + "TTTTTTT" + "ACG" * 5, ref._config(False, True)))
+    assert recs and all(isinstance(r, finders.TandemRepeat) for r in recs)
+
+
+def test_row_chain_homopolymer_shortcut_equals_generic_path():
+    """rowchain.finish_rows settles isolated homopolymer merge events on integers (FAST_K1); with the shortcut
+    off every candidate goes through _should_merge_repeats / _recompute_repeat.  Same calls either way, on
+    run-length rows of random and of low-complexity text (dense events, chains of events, contig ends)."""
+    import dataclasses
+
+    from bwt_algorithm_b200 import pipeline, rowchain
+
+    cfg = {"sa_sample_rate": 32, "show_progress": False, "allow_mismatches": True, "max_motif_length": 9,
+           "min_period": 10, "max_period": 1000, "min_copies": 3, "min_entropy": 1.0, "max_unit_len": 120}
+    rng = np.random.default_rng(11)
+    texts = {
+        "random_300k": np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 300_000)],
+        "at_rich": np.frombuffer(b"AATTAC", np.uint8)[rng.integers(0, 6, 120_000)],
+        "two_letters": np.frombuffer(b"AT", np.uint8)[rng.integers(0, 2, 60_000)],
+        "with_N": np.frombuffer(b"ACGTNN", np.uint8)[rng.integers(0, 6, 80_000)],
+        "ends_in_runs": np.concatenate([np.full(7, 65, np.uint8), np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 5000)],
+                                        np.full(4, 84, np.uint8), np.full(5, 65, np.uint8)]),
+    }
+    total_events = 0
+    for name, s in texts.items():
+        for trim in (0, 30):
+            n = s.size
+            d = np.flatnonzero(np.diff(s) != 0) + 1
+            starts, ends = np.concatenate(([0], d)), np.concatenate((d, [n]))
+            sel = (ends - starts >= 3) & (starts >= trim) & (ends <= n - trim)
+            rows = np.zeros((int(sel.sum()), 8), np.int32)
+            rows[:, 0], rows[:, 1], rows[:, 2] = starts[sel] - trim, ends[sel] - trim, 1
+            rows[:, 3], rows[:, 6] = (ends - starts)[sel], 1
+            # a few longer-unit rows on top (they take part in suppression and collapse)
+            extra = rows[:: max(1, len(rows) // 50)].copy()
+            extra[:, 1] = np.minimum(extra[:, 0] + 12, n - 2 * trim)
+            extra[:, 2], extra[:, 3], extra[:, 6] = 4, 3, 4
+            extra = extra[extra[:, 1] - extra[:, 0] == 12]
+            rows = np.concatenate([rows, extra])
+            seq = s.tobytes().decode()
+            body = seq[trim:n - trim] if trim else seq
+            text = np.frombuffer((body + "$").encode(), np.uint8)
+            f = pipeline._contig_finder("c1", body, cfg, seq[:trim], seq[n - trim:] if trim else "")
+            fast = rowchain.finish_rows(f, "c1", text, rows)
+            slow = rowchain._finish_rows_slow(pipeline._contig_finder("c1", body, cfg, seq[:trim], seq[n - trim:] if trim else ""),
+                                              "c1", text, rows)
+            assert fast[1:] == slow[1:], name
+            assert [dataclasses.astuple(r) for r in fast[0]] == [dataclasses.astuple(r) for r in slow[0]], name
+            total_events += len(slow[0])
+    assert total_events > 1000

@@ -1,0 +1,52 @@
+"""Wall time of the drop-in CLI on a chr21-sized synthetic FASTA:
+
+    python tools/cli_time.py [--n 46709983] [--format bed]
+
+writes the FASTA (SURVEY Appendix B generator, 80 columns), runs `python bwt.py <fa> --progress --format F -o out`
+as a subprocess and prints one JSON line with the wall time, the record count and the md5 of the output."""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=46_709_983)
+    ap.add_argument("--format", default="bed")
+    ap.add_argument("--jobs", default="4")
+    args = ap.parse_args()
+    import numpy as np
+
+    from bench import gen_contig
+
+    s = gen_contig(args.n, 21)
+    tmp = tempfile.mkdtemp(prefix="bwtk_cli_")
+    fa, out = os.path.join(tmp, "chr21_sized.fa"), os.path.join(tmp, "out." + args.format)
+    pad = (-s.size) % 80
+    body = np.concatenate([s, np.full(pad, 10, np.uint8)]).reshape(-1, 80)
+    lines = np.concatenate([body, np.full((body.shape[0], 1), 10, np.uint8)], axis=1).tobytes()
+    with open(fa, "wb") as fh:
+        fh.write(b">chr21_sized synthetic\n" + lines.rstrip(b"\n") + b"\n")
+    t0 = time.perf_counter()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bwt.py"), fa, "--progress", "--format", args.format,
+                          "--jobs", args.jobs, "-o", out], capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    ok = res.returncode == 0 and os.path.exists(out)
+    md5 = hashlib.md5(open(out, "rb").read()).hexdigest() if ok else None
+    nrec = sum(1 for _ in open(out)) if ok else 0
+    tail = [ln for ln in res.stdout.splitlines() if "Strict adjacency" in ln or "Nested call" in ln or "Completed" in ln]
+    print(json.dumps({"cli": f"python bwt.py chr21_sized.fa --progress --format {args.format} --jobs {args.jobs}",
+                      "bases": args.n, "wall_s": round(dt, 2), "rc": res.returncode, "output_lines": nrec, "md5": md5,
+                      "stdout": tail[-3:], "stderr_tail": res.stderr[-300:]}))
+
+
+if __name__ == "__main__":
+    main()
