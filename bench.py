@@ -704,7 +704,7 @@ def run_reference(args):
     orc.build()
     cores = min(os.cpu_count() or 1, args.cpu_cores)
     times = []
-    WINDOW = REF_WINDOW
+    WINDOW = args.ref_window
     with _pool(cores) as pool:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
@@ -717,7 +717,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     base = {"value": round(value, 9), "unit": "Gbases/s", "cores": cores, "kind": "port",
             "sample": f"per step: {cores} processes x one {WINDOW}-base window (index + Tier 1 + Tier 2, oracle port)"}
-    ref = python_reference_sample()
+    ref = None if args.no_python_ref else python_reference_sample()
     if ref is not None:
         base["python_reference"] = ref
     out = {
@@ -744,6 +744,10 @@ def main():
     ap.add_argument("--fm-log2-queries", type=int, default=26, help="random 10-mers of the FM section (2^k)")
     ap.add_argument("--cpu-cores", type=int, default=64, help="upper bound on host processes of the CPU legs")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-window", type=int, default=REF_WINDOW,
+                    help="bases per window (one per core and step) of the reference arm")
+    ap.add_argument("--no-python-ref", action="store_true",
+                    help="skip the 1 Mb sample of the unmodified Python reference (baseline/_ref/bwt.py)")
     ap.add_argument("--skip-extras", action="store_true",
                     help="genome steps only (no per-kernel profile, FM search or scan sections); used under ncu")
     args = ap.parse_args()

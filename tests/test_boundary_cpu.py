@@ -217,7 +217,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     import sys
 
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--cpu-sample", "40000"], capture_output=True, text=True, timeout=300)
+                          "--warmup", "0", "--ref-window", "3000", "--cpu-cores", "4", "--no-python-ref"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "SA+BWT+LCP Gbases/s" and line["unit"] == "Gbases/s"
