@@ -275,9 +275,13 @@ struct RowMap {
 
 // One warp per checkpoint block: gathers the block's BWT bytes, stores them, and
 // writes the block's per-row symbol counts into occ[row][blk+1] (prefix-summed
-// later, in place).
+// later, in place).  PACKED (ACGT$ texts): the symbol comes from the 2-bit text -- a quarter of
+// the bytes, so that the random gathers of a chromosome-sized contig (62 MB packed against
+// 249 MB of bytes) stay inside the 126 MB L2; the '$' that precedes suffix 0 is the one special case.
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
-    bwt_block_kernel(const uint8_t *__restrict__ text, const int32_t *__restrict__ sa, int64_t n, int occ_rate,
+    bwt_block_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ packed,
+                     const int32_t *__restrict__ sa, int64_t n, int occ_rate,
                      RowMap rows, int nrows, uint8_t *__restrict__ bwt, int32_t *__restrict__ occ, int64_t ncp,
                      int64_t nblk)
 {
@@ -298,8 +302,13 @@ __global__ void __launch_bounds__(256)
                 uint8_t c;
                 if (rg == 0) {
                     int64_t p = (int64_t)__ldg(sa + j) - 1;
-                    if (p < 0) p += n;
-                    c = __ldg(text + p);
+                    if (PACKED) {
+                        const uint32_t code = p >= 0 ? (__ldg(packed + (p >> 4)) >> (30 - 2 * (int)(p & 15))) & 3u : 4u;
+                        c = (uint8_t)((0x2454474341ull >> (8 * code)) & 0xffu);   // "ACGT$"
+                    } else {
+                        if (p < 0) p += n;
+                        c = __ldg(text + p);
+                    }
                     bwt[j] = c;
                 } else {
                     c = bwt[j];
@@ -403,8 +412,8 @@ __global__ void __launch_bounds__(1024) occ_scan_kernel(int32_t *__restrict__ oc
 }
 
 // d_partial: nrows * OCC_SEGS ints of scratch
-static int launch_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n, int occ_rate, const RowMap &rows,
-                          int nrows, uint8_t *d_bwt, int32_t *d_occ, int *d_partial, cudaStream_t st)
+static int launch_bwt_occ(const uint8_t *d_text, const uint32_t *d_packed2, const int32_t *d_sa, int64_t n, int occ_rate,
+                          const RowMap &rows, int nrows, uint8_t *d_bwt, int32_t *d_occ, int *d_partial, cudaStream_t st)
 {
     int64_t nblk = ceil_div(n, occ_rate);
     int64_t ncp = n / occ_rate + 1 + (n % occ_rate != 0);
@@ -412,7 +421,12 @@ static int launch_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int64_t n,
     if (grid > NUM_SMS * 16) grid = NUM_SMS * 16;
     {
         prof::Scope ps("bwt_block_kernel", n * 5 + (int64_t)nrows * ncp * 4, st);
-        bwt_block_kernel<<<(unsigned)grid, 256, 0, st>>>(d_text, d_sa, n, occ_rate, rows, nrows, d_bwt, d_occ, ncp, nblk);
+        if (d_packed2)   // 2-bit ACGT$ layout of the text (position n-1, the '$', is packed as code 0 and never read)
+            bwt_block_kernel<true><<<(unsigned)grid, 256, 0, st>>>(d_text, d_packed2, d_sa, n, occ_rate, rows, nrows, d_bwt,
+                                                                   d_occ, ncp, nblk);
+        else
+            bwt_block_kernel<false><<<(unsigned)grid, 256, 0, st>>>(d_text, nullptr, d_sa, n, occ_rate, rows, nrows, d_bwt,
+                                                                    d_occ, ncp, nblk);
     }
     BWTK_LAUNCH_CHECK();
     {
@@ -577,7 +591,7 @@ extern "C" int32_t bwtk_bwt_occ(const uint8_t *d_text, const int32_t *d_sa, int6
     BWTK_REQUIRE(ws_bytes >= bwtk_bwt_occ_workspace_bytes(n, occ_rate, nrows), "workspace too small");
     RowMap rm;
     BWTK_REQUIRE(make_rowmap(h_row_of_code, &rm) == 0, "row_of_code entries must be in [-1, 255]");
-    return launch_bwt_occ(d_text, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, (int *)d_ws, st);
+    return launch_bwt_occ(d_text, nullptr, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, (int *)d_ws, st);
 }
 
 extern "C" int64_t bwtk_lcp_workspace_bytes(int64_t n)
@@ -664,7 +678,7 @@ extern "C" int32_t bwtk_index_build(const uint8_t *d_text, int64_t n, int32_t oc
     if (rc) return rc;
     if (h_stats) h_stats[7] = nrows;
     if (d_bwt && d_occ) {
-        rc = launch_bwt_occ(d_text, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, d_partial, st);
+        rc = launch_bwt_occ(d_text, fast ? packed : nullptr, d_sa, n, occ_rate, rm, nrows, d_bwt, d_occ, d_partial, st);
         if (rc) return rc;
     }
     if (d_lcp) {

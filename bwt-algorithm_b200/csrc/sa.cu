@@ -21,6 +21,9 @@
 // The host reads the active count once per round (4 bytes) to size the grids and
 // to pick the sort.  The result is the unique suffix array, so it is bit-identical
 // to the reference's regardless of the refinement path taken.
+#include <stdlib.h>
+
+#include "bucket_sort.cuh"
 #include "radix_sort.cuh"
 
 namespace bwtk {
@@ -82,6 +85,30 @@ struct LazyRank {
         if ((__ldg(abits + (x >> 5)) >> (x & 31)) & 1u) return __ldg(rank + x);
         uint32_t key = window32(packed, x * bits);
         int32_t lo = __ldg(ptab + (key >> 16)), hi = __ldg(ptab + (key >> 16) + 1);
+        // lower bound of key in skey[lo, hi).  On a chromosome-sized contig the range is thousands of keys and
+        // every probe of a plain binary search is its own DRAM sector: start from the interpolated place (the
+        // low 16 key bits are close to uniform inside one prefix) and gallop out, so that all but the first
+        // probes fall into the same two or three sectors.
+        if (hi - lo > 32) {
+            const int32_t p = lo + (int32_t)(((uint64_t)(key & 0xffffu) * (uint32_t)(hi - lo)) >> 16);
+            int32_t step = 16;
+            if (__ldg(skey + p) < key) {
+                lo = p + 1;
+                while (true) {
+                    const int32_t q = lo + step;
+                    if (q < hi && __ldg(skey + q) < key) { lo = q + 1; step <<= 1; }
+                    else { hi = q < hi ? q : hi; break; }
+                }
+            } else {
+                hi = p;
+                while (true) {
+                    const int32_t q = hi - step;
+                    if (q <= lo) break;
+                    if (__ldg(skey + q) >= key) { hi = q; step <<= 1; }
+                    else { lo = q + 1; break; }
+                }
+            }
+        }
         while (lo < hi) {
             int32_t mid = (lo + hi) >> 1;
             if (__ldg(skey + mid) < key) lo = mid + 1; else hi = mid;
@@ -467,6 +494,23 @@ static int bits_for(int64_t v)  // bits needed to represent values 0..v
 
 }  // namespace sa
 
+// Round 0 goes through the MSD bucket sort for 2-bit texts from BWTK_MSD_MIN_N symbols on (below that the
+// 8192 sort CTAs are mostly empty and the four LSD passes are cheaper).  BWTK_MSD=0 / BWTK_MSD_FUSE=0 switch
+// the path / the fused regroup off (tuning and tests).
+static bool msd_enabled(int64_t n)
+{
+    const char *e = getenv("BWTK_MSD");
+    if (e && atoi(e) == 0) return false;
+    const char *m = getenv("BWTK_MSD_MIN_N");
+    const int64_t min_n = m ? atoll(m) : (1ll << 21);
+    return n >= min_n;
+}
+static bool msd_fuse_enabled()
+{
+    const char *e = getenv("BWTK_MSD_FUSE");
+    return !(e && atoi(e) == 0);
+}
+
 // Workspace of the doubling rounds (the packed text is provided by the caller).
 int64_t sa_core_workspace_bytes(int64_t n)
 {
@@ -483,6 +527,7 @@ int64_t sa_core_workspace_bytes(int64_t n)
     b += align_up(ceil_div(n, sa::RG_TILE) * 8 + 256, 256);  // regroup status
     b += rsort::workspace_bytes(n);
     b += 8192 + align_up((int64_t)sizeof(sa::SegCtl), 256);  // counters, segmented-sort control block
+    b += msd::workspace_bytes(n) + 1024;   // round-0 bucket sort (bucket_sort.cuh)
     return b;
 }
 
@@ -525,6 +570,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     rsort::Workspace rws = rsort::carve(c, n);
     unsigned *counters = c.take<unsigned>(sa::MAX_ROUNDS + 8);  // [0] regroup tile id, [1+r] active count entering round r
     sa::SegCtl *ctl = c.take<sa::SegCtl>(1);
+    msd::Workspace mws = msd::carve(c, n);
     if (!c.ok()) {
         set_error("sa workspace carve overflow");
         return BWTK_EWORKSPACE;
@@ -537,19 +583,37 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
     BWTK_CUDA(bwtk::zero_async(abits, (size_t)(n / 32 + 2) * 4, st));
     int64_t passes = 0;
     int in_first = 1;
-    // round-0 ping-pong buffers chosen so that the sorted keys land in `skeep`
-    // (the generator pass writes k0; an odd number of passes ends in k0)
-    const bool odd = (rsort::make_plan(0, S * bits).passes & 1) != 0;
-    uint32_t *key32a = odd ? skeep : (uint32_t *)keyA, *key32b = odd ? (uint32_t *)keyA : skeep;
-    {
-        // round 0: the histogram and the first radix pass read the suffix keys
+    uint32_t *skey32 = nullptr, *sval = nullptr, *suf_other = nullptr;
+    int32_t *pos_in = pos0, *pos_out = pos1;
+    bool msd_done = false, msd_fused = false;
+    if (bits == 2 && msd_enabled(n)) {
+        // round 0 as an MSD bucket sort that only moves positions (bucket_sort.cuh); with no oversize
+        // bucket it also does the first regroup pass
+        // scratch of the oversize pass: pos0 is free either way; fused, the active list goes to (pos_out, val1, grp)
+        // and val0 is free; unfused, val0 receives the sorted suffixes and val1 is free
+        const bool fuse = msd_fuse_enabled();
+        msd::Regroup rg{d_sa, rank, pos_out, val1, grp, abits, ptab, nullptr, d_counts + 1, rws.err, nullptr};
+        int rc = msd::round0_sort(packed, n, mws, rws, reinterpret_cast<uint2 *>(keyA), reinterpret_cast<uint2 *>(keyB),
+                                  skeep, val0, reinterpret_cast<uint32_t *>(pos0), fuse ? val0 : val1, fuse ? &rg : nullptr,
+                                  ptab, n - S + 1, st, &msd_done, &msd_fused, &passes);
+        if (rc) return rc;
+        if (msd_done) { skey32 = skeep; sval = val0; suf_other = val1; }
+    }
+    if (!msd_done) {
+        // round-0 ping-pong buffers chosen so that the sorted keys land in `skeep`
+        // (the generator pass writes k0; an odd number of passes ends in k0)
+        const bool odd = (rsort::make_plan(0, S * bits).passes & 1) != 0;
+        uint32_t *key32a = odd ? skeep : (uint32_t *)keyA, *key32b = odd ? (uint32_t *)keyA : skeep;
+        // the histogram and the first radix pass read the suffix keys
         // straight from the packed text (no key/value arrays are materialised)
         rsort::PackedSuffixSource src{packed, n, bits, S * bits};
         int rc = rsort::sort_pairs_from<uint32_t, rsort::PackedSuffixSource>(src, false, key32a, val0, key32b, val1, n,
                                                                             0, S * bits, rws, st, &in_first, &passes);
         if (rc) return rc;
+        skey32 = in_first ? key32a : key32b;
+        sval = in_first ? val0 : val1;
+        suf_other = in_first ? val1 : val0;  // free value buffer receives the active suffixes
     }
-    uint32_t *skey32 = in_first ? key32a : key32b;
     // key of the suffix at every SA position (later rounds only permute suffixes inside a
     // group of equal keys); stays valid until the caller reuses the workspace
     if (d_skey0_out) *d_skey0_out = skey32;
@@ -559,10 +623,7 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
         *d_free_out = keyB;
         *free_bytes_out = (int64_t)((char *)d_ws + ws_bytes - (char *)keyB);
     }
-    uint32_t *sval = in_first ? val0 : val1;
-    int32_t *pos_in = pos0, *pos_out = pos1;
-    uint32_t *suf_other = in_first ? val1 : val0;  // free value buffer receives the active suffixes
-    {
+    if (!msd_fused) {
         int64_t tiles = ceil_div(n, sa::RG_TILE);
         BWTK_CUDA(bwtk::zero_async(rg_status, (size_t)tiles * 8, st));
         {
@@ -685,7 +746,8 @@ int sa_build_core(const uint32_t *packed, int64_t n, int bits, bool fast, int32_
             rounds++;
         }
         h_stats[0] = rounds; h_stats[1] = bits; h_stats[2] = S; h_stats[3] = active0;
-        h_stats[4] = sum_active; h_stats[5] = passes; h_stats[6] = fast ? 1 : 0;
+        h_stats[4] = sum_active; h_stats[5] = passes;
+        h_stats[6] = (fast ? 1 : 0) | (msd_done ? 2 : 0) | (msd_fused ? 4 : 0);   // bit 1: round 0 by bucket sort, bit 2: fused regroup
     }
     return BWTK_OK;
 }

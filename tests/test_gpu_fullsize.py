@@ -147,7 +147,7 @@ def chr21(torch):
 
 def test_chr21_index_properties(torch, chr21):
     text, ix = chr21
-    assert ix.n == CHR21 + 1 and ix.sa_stats[6] == 1
+    assert ix.n == CHR21 + 1 and (ix.sa_stats[6] & 1) == 1
     _check_index_properties(torch, ix, ix.text)
     torch.cuda.empty_cache()
 
