@@ -371,6 +371,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    scanner.profile_phases = True          # one untimed pass with events around every phase (rank-local breakdown)
+    genome_step(dev_texts, False)
+    phase_ms = dict(scanner.phase_ms)
+    scanner.profile_phases = False
     dev_ms, dev_scan_ms, launches, res, rows, merged = timed_steps(dev_texts, False, args.steps)
     e2e_ms, e2e_scan_ms, e2e_launches, res, rows, merged = timed_steps(host_texts, True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -558,6 +562,7 @@ def run_ours(args):
             "per_rank_ms": [round(float(x[0]) / steps, 3) for x in allt],
             "per_rank_scan_ms": [round(float(x[2]) / steps, 3) for x in allt],
             "rows": {k: int(sum(float(x[9 + j]) for x in allt)) for j, k in enumerate(KINDS)},
+            "phase_ms_rank0": {k: round(v, 3) for k, v in phase_ms.items()},
             "gpu_launches": int(sum(float(x[8]) for x in allt)),
             "clocks": clocks,
             "roofline": roof,

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(THREADS)
 // Units with (mc-1)*u < 8: one thread per position, run starts found directly.
 __global__ void __launch_bounds__(256)
     find_runs_small_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t u_lo, int64_t u_hi,
-                           int64_t mc, CandOut out)
+                           int64_t mc, int64_t min_run_u1, CandOut out)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -323,8 +323,115 @@ __global__ void __launch_bounds__(256)
         if (i > 0 && __ldg(text + i - 1) == __ldg(text + i - 1 + u)) continue;  // not a run start
         int64_t b = i + 1;
         while (b < lim && __ldg(text + b) == __ldg(text + b + u)) b++;
-        if (b - i >= (mc - 1) * u) push_cand(out, u, i, b);
+        if (b - i >= (u == 1 && min_run_u1 > mc - 1 ? min_run_u1 : (mc - 1) * u)) push_cand(out, u, i, b);
     }
+}
+
+// ---- small units, ordered: the maximal runs of ONE unit length u (<= 7 positions) in text order ------
+// The per-position kernel above pushes every run through one global counter and leaves the list to be
+// sorted; homopolymer runs alone are ~5 % of the positions.  Here a scan (scan.cuh) over 16-position
+// chunks counts the qualifying run starts of a chunk from one match mask (two 16-byte loads, byte-wise
+// compares on 64-bit words), and the emit phase writes them at their place in the sorted list: no
+// atomics, no sort, and the list of the large units that does get sorted stays short.
+template <int U> struct SmallRuns {
+    const uint8_t *text;    // 16-byte aligned
+    int64_t n;
+    int64_t L;              // minimum run length
+    // bit j: text[p0 + j] == text[p0 + j + U] (and p0 + j < n - U), j = 0..15; *prev: the same for p0 - 1
+    __device__ __forceinline__ uint32_t mask(int64_t p0, bool *prev) const
+    {
+        const int64_t lim = n - U;
+        uint32_t e = 0;
+        if (p0 + 32 <= n) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(text + p0));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(text + p0 + 16));
+            const unsigned long long w0 = ((unsigned long long)a.y << 32) | a.x, w1 = ((unsigned long long)a.w << 32) | a.z,
+                                     w2 = ((unsigned long long)b.y << 32) | b.x;
+            // bytes j + U of the two 8-byte halves
+            const unsigned long long s0 = (w0 >> (8 * U)) | (w1 << (64 - 8 * U)), s1 = (w1 >> (8 * U)) | (w2 << (64 - 8 * U));
+            unsigned long long x0 = w0 ^ s0, x1 = w1 ^ s1;
+            // zero bytes -> bit 7 of the byte (exact form: no borrow across bytes)
+            const unsigned long long K = 0x7f7f7f7f7f7f7f7full;
+            x0 = ~(((x0 & K) + K) | x0 | K);
+            x1 = ~(((x1 & K) + K) | x1 | K);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                e |= (uint32_t)((x0 >> (8 * j + 7)) & 1ull) << j;
+                e |= (uint32_t)((x1 >> (8 * j + 7)) & 1ull) << (8 + j);
+            }
+            if (p0 + 16 > lim) e &= lim > p0 ? ((1u << (int)(lim - p0)) - 1u) : 0u;
+        } else {
+            for (int j = 0; j < 16; j++) {
+                const int64_t q = p0 + j;
+                if (q < lim && __ldg(text + q) == __ldg(text + q + U)) e |= 1u << j;
+            }
+        }
+        *prev = p0 > 0 && p0 - 1 < lim && __ldg(text + p0 - 1) == __ldg(text + p0 - 1 + U);
+        return e;
+    }
+    // calls f(start, end) for every maximal run of >= L matches that starts in the chunk
+    template <typename F> __device__ __forceinline__ void for_runs(int64_t c, F f) const
+    {
+        const int64_t p0 = c * 16;
+        if (p0 >= n - U) return;
+        bool prev;
+        const uint32_t e = mask(p0, &prev);
+        uint32_t starts = e & ~((e << 1) | (prev ? 1u : 0u)) & 0xffffu;
+        const int64_t lim = n - U;
+        while (starts) {
+            const int j = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const uint32_t rest = ~(e >> j);                 // first mismatch after j
+            int t = __ffs(rest) - 1;                          // e has 16 bits: a zero always exists at or below bit 16 - j
+            int64_t b = p0 + j + t;
+            if (j + t >= 16) {                                // the run leaves the chunk
+                b = p0 + 16;
+                while (b < lim && __ldg(text + b) == __ldg(text + b + U)) b++;
+            }
+            if (b - (p0 + j) >= L) f(p0 + j, b);
+        }
+    }
+};
+template <int U> struct SmallRunsCount {
+    SmallRuns<U> sr;
+    __device__ unsigned long long operator()(int64_t c) const
+    {
+        unsigned cnt = 0;
+        sr.for_runs(c, [&](int64_t, int64_t) { cnt++; });
+        return cnt;
+    }
+};
+template <int U> struct SmallRunsEmit {
+    SmallRuns<U> sr;
+    CandOut out;
+    const unsigned long long *base;   // device: runs already in the list
+    __device__ void operator()(int64_t c, unsigned long long excl, unsigned long long cnt) const
+    {
+        if (!cnt) return;
+        unsigned long long at = *base + excl;
+        sr.for_runs(c, [&](int64_t a, int64_t b) {
+            if ((int64_t)at < out.cap) {
+                out.key[at] = ((unsigned long long)(out.umax - U) << out.abits) | (unsigned long long)a;
+                out.val[at] = (uint32_t)b;
+            }
+            at++;
+        });
+    }
+};
+static __global__ void add_total_kernel(unsigned long long *base, const unsigned long long *total) { *base += *total; }
+
+template <int U>
+static int small_runs_append(const uint8_t *d_text, int64_t n, int64_t L, const CandOut &out, unsigned long long *d_base,
+                             const scan::Workspace &sws, cudaStream_t st)
+{
+    SmallRuns<U> sr{d_text, n, L};
+    SmallRunsCount<U> cf{sr};
+    SmallRunsEmit<U> ef{sr, out, d_base};
+    int rc = scan::run(ceil_div(n, 16), cf, ef, sws, st);
+    if (rc) return rc;
+    add_total_kernel<<<1, 1, 0, st>>>(d_base, sws.total);
+    BWTK_LAUNCH_CHECK();
+    return BWTK_OK;
 }
 
 struct Resolved {
@@ -419,18 +526,21 @@ static int64_t cand_capacity(int64_t n) { return n / 2 + 65536; }
 static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t u_hi, int64_t mc,
                         unsigned long long *key0, unsigned long long *key1, uint32_t *val0, uint32_t *val1,
                         unsigned long long *d_count, int64_t ccap, const rsort::Workspace &rws, cudaStream_t st,
-                        const unsigned long long **sk, const uint32_t **sv, int64_t *m)
+                        const unsigned long long **sk, const uint32_t **sv, int64_t *m,
+                        const scan::Workspace *sws = nullptr, int64_t min_run_u1 = 0)
 {
     *m = 0;
     BWTK_CUDA(bwtk::zero_async(d_count, 16, st));
     CandOut out;
     out.key = key0; out.val = val0; out.count = d_count; out.cap = ccap;
     out.abits = bits_for(n); out.umax = u_hi;
-    // units with (mc-1)*u < 8 take the per-position kernel, the rest the ballot kernel
+    // units with (mc-1)*u < 8 take the per-position search, the rest the ballot kernel
     int64_t small_hi = 7 / (mc - 1);
     if (small_hi > u_hi) small_hi = u_hi;
-    if (small_hi >= u_lo) {
-        find_runs_small_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_text, n, u_lo, small_hi, mc, out);
+    // ordered form (no atomics, no sort) when a scan workspace is given and the text allows 16-byte loads
+    const bool ordered = sws != nullptr && small_hi >= u_lo && small_hi <= 7 && (((uintptr_t)d_text) & 15) == 0;
+    if (small_hi >= u_lo && !ordered) {
+        find_runs_small_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_text, n, u_lo, small_hi, mc, min_run_u1, out);
         BWTK_LAUNCH_CHECK();
     }
     int64_t big_lo = small_hi + 1 > u_lo ? small_hi + 1 : u_lo;
@@ -483,13 +593,37 @@ static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t 
     { int rc = read_back(&h_cand, d_count, 8, st); if (rc) return rc; }
     *m = (int64_t)h_cand;
     if ((int64_t)h_cand > ccap) return BWTK_EWORKSPACE;
-    if (h_cand == 0) return BWTK_OK;
     int in_first = 1;
-    int rc = rsort::sort_pairs<unsigned long long>(key0, val0, key1, val1, (int64_t)h_cand, 0,
-                                                   out.abits + bits_for(u_hi), rws, st, &in_first, nullptr);
-    if (rc) return rc;
+    if (h_cand > 1) {
+        int rc = rsort::sort_pairs<unsigned long long>(key0, val0, key1, val1, (int64_t)h_cand, 0,
+                                                       out.abits + bits_for(u_hi), rws, st, &in_first, nullptr);
+        if (rc) return rc;
+    }
     *sk = in_first ? key0 : key1;
     *sv = in_first ? val0 : val1;
+    if (ordered) {
+        // the small units follow the sorted large ones in the list: u = small_hi first (smaller key), u_lo last
+        CandOut tail = out;
+        tail.key = in_first ? key0 : key1;
+        tail.val = in_first ? val0 : val1;
+        for (int64_t u = small_hi; u >= u_lo; u--) {
+            const int64_t L = u == 1 && min_run_u1 > mc - 1 ? min_run_u1 : (mc - 1) * u;
+            int rc = BWTK_OK;
+            switch (u) {
+            case 1: rc = small_runs_append<1>(d_text, n, L, tail, d_count, *sws, st); break;
+            case 2: rc = small_runs_append<2>(d_text, n, L, tail, d_count, *sws, st); break;
+            case 3: rc = small_runs_append<3>(d_text, n, L, tail, d_count, *sws, st); break;
+            case 4: rc = small_runs_append<4>(d_text, n, L, tail, d_count, *sws, st); break;
+            case 5: rc = small_runs_append<5>(d_text, n, L, tail, d_count, *sws, st); break;
+            case 6: rc = small_runs_append<6>(d_text, n, L, tail, d_count, *sws, st); break;
+            default: rc = small_runs_append<7>(d_text, n, L, tail, d_count, *sws, st); break;
+            }
+            if (rc) return rc;
+        }
+        { int rc = read_back(&h_cand, d_count, 8, st); if (rc) return rc; }
+        *m = (int64_t)h_cand;
+        if ((int64_t)h_cand > ccap) return BWTK_EWORKSPACE;
+    }
     return BWTK_OK;
 }
 
@@ -624,51 +758,93 @@ struct RunCand {
     }
 };
 
-// one warp per run: number of candidates of every run
+// Candidates of every run.  Most runs span a handful of positions: one THREAD per run walks them; runs of
+// more than RUN_SHORT positions are left to a second launch with one WARP per run (32 positions per step).
+constexpr int RUN_SHORT = 48;
+
 __global__ void __launch_bounds__(256)
     run_count_kernel(RunCand rc, int64_t nruns, uint32_t *__restrict__ cnt)
 {
-    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= nruns) return;
-    const int lane = threadIdx.x & 31;
     int64_t ra, rb, hi;
     rc.bounds(r, ra, rb, hi);
+    if (hi - ra >= RUN_SHORT) return;          // the warp kernel's
     uint32_t total = 0;
-    if (rc.motif_is_acgt(ra)) {
-        for (int64_t i0 = ra; i0 <= hi; i0 += 32) {
-            const int64_t i = i0 + lane;
-            const bool ok = i <= hi && rc.test(i, rb) >= 0;
-            total += (uint32_t)__popc(__ballot_sync(0xffffffffu, ok));
-        }
-    }
-    if (lane == 0) cnt[r] = total;
+    if (hi >= ra && rc.motif_is_acgt(ra))
+        for (int64_t i = ra; i <= hi; i++) total += rc.test(i, rb) >= 0 ? 1u : 0u;
+    cnt[r] = total;
 }
 
-// one warp per run: the candidates in ascending position order at off[r]..
+__global__ void __launch_bounds__(256)
+    run_count_long_kernel(RunCand rc, int64_t nruns, uint32_t *__restrict__ cnt)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < nruns; r += (int64_t)gridDim.x * 8) {
+        int64_t ra, rb, hi;
+        rc.bounds(r, ra, rb, hi);
+        if (hi - ra < RUN_SHORT) continue;
+        uint32_t total = 0;
+        if (rc.motif_is_acgt(ra)) {
+            for (int64_t i0 = ra; i0 <= hi; i0 += 32) {
+                const int64_t i = i0 + lane;
+                const bool ok = i <= hi && rc.test(i, rb) >= 0;
+                total += (uint32_t)__popc(__ballot_sync(0xffffffffu, ok));
+            }
+        }
+        if (lane == 0) cnt[r] = total;
+    }
+}
+
+// the candidates in ascending position order at off[r]..
 __global__ void __launch_bounds__(256)
     run_emit_kernel(RunCand rc, int64_t nruns, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ off,
                     int32_t *__restrict__ cpos, int32_t *__restrict__ cend, unsigned long long *__restrict__ ckey,
                     uint32_t *__restrict__ cidx, int64_t step)
 {
-    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= nruns) return;
     if (cnt[r] == 0) return;
-    const int lane = threadIdx.x & 31;
     int64_t ra, rb, hi;
     rc.bounds(r, ra, rb, hi);
-    uint32_t at = off[r];
-    for (int64_t i0 = ra; i0 <= hi; i0 += 32) {
-        const int64_t i = i0 + lane;
-        const int64_t e = i <= hi ? rc.test(i, rb) : -1;
-        const unsigned bal = __ballot_sync(0xffffffffu, e >= 0);
+    if (hi - ra >= RUN_SHORT) return;
+    uint32_t s = off[r];
+    for (int64_t i = ra; i <= hi; i++) {
+        const int64_t e = rc.test(i, rb);
         if (e >= 0) {
-            const uint32_t s = at + (uint32_t)__popc(bal & lanemask_lt());
             cpos[s] = (int32_t)i;
             cend[s] = (int32_t)e;
             ckey[s] = ((unsigned long long)(i % step) << rc.abits) | (unsigned long long)i;
             cidx[s] = s;
+            s++;
         }
-        at += (uint32_t)__popc(bal);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    run_emit_long_kernel(RunCand rc, int64_t nruns, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ off,
+                         int32_t *__restrict__ cpos, int32_t *__restrict__ cend, unsigned long long *__restrict__ ckey,
+                         uint32_t *__restrict__ cidx, int64_t step)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < nruns; r += (int64_t)gridDim.x * 8) {
+        int64_t ra, rb, hi;
+        rc.bounds(r, ra, rb, hi);
+        if (hi - ra < RUN_SHORT || cnt[r] == 0) continue;
+        uint32_t at = off[r];
+        for (int64_t i0 = ra; i0 <= hi; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const int64_t e = i <= hi ? rc.test(i, rb) : -1;
+            const unsigned bal = __ballot_sync(0xffffffffu, e >= 0);
+            if (e >= 0) {
+                const uint32_t s = at + (uint32_t)__popc(bal & lanemask_lt());
+                cpos[s] = (int32_t)i;
+                cend[s] = (int32_t)e;
+                ckey[s] = ((unsigned long long)(i % step) << rc.abits) | (unsigned long long)i;
+                cidx[s] = s;
+            }
+            at += (uint32_t)__popc(bal);
+        }
     }
 }
 
@@ -964,14 +1140,19 @@ static int greedy_pass_runs(const RunCand &rcand, int64_t nruns, int64_t limit, 
     *emitted = 0;
     if (nruns <= 0) return BWTK_OK;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(w.j0), *off = reinterpret_cast<uint32_t *>(w.j1);   // free until the replay
-    run_count_kernel<<<(unsigned)ceil_div(nruns, 8), 256, 0, st>>>(rcand, nruns, cnt);
+    const unsigned long_grid = (unsigned)(ceil_div(nruns, 8) < NUM_SMS * 16 ? ceil_div(nruns, 8) : NUM_SMS * 16);
+    run_count_kernel<<<(unsigned)ceil_div(nruns, 256), 256, 0, st>>>(rcand, nruns, cnt);
+    BWTK_LAUNCH_CHECK();
+    run_count_long_kernel<<<long_grid, 256, 0, st>>>(rcand, nruns, cnt);
     BWTK_LAUNCH_CHECK();
     CountArr ca{cnt};
     StoreOffset so{off};
     int rc = scan::run(nruns, ca, so, w.sws, st);
     if (rc) return rc;
-    run_emit_kernel<<<(unsigned)ceil_div(nruns, 8), 256, 0, st>>>(rcand, nruns, cnt, off, w.cpos, w.cend, w.ckey0,
-                                                                 w.cidx0, step);
+    run_emit_kernel<<<(unsigned)ceil_div(nruns, 256), 256, 0, st>>>(rcand, nruns, cnt, off, w.cpos, w.cend, w.ckey0,
+                                                                   w.cidx0, step);
+    BWTK_LAUNCH_CHECK();
+    run_emit_long_kernel<<<long_grid, 256, 0, st>>>(rcand, nruns, cnt, off, w.cpos, w.cend, w.ckey0, w.cidx0, step);
     BWTK_LAUNCH_CHECK();
     unsigned long long hK = 0;
     rc = read_back(&hK, w.sws.total, 8, st);
@@ -1202,7 +1383,7 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
     const uint32_t *sv = nullptr;
     int64_t m = 0;
     int rc = strict::collect_runs(d_text, n, min_unit_len, umax, min_copies, key0, key1, val0, val1, d_count, ccap, rws,
-                                  st, &sk, &sv, &m);
+                                  st, &sk, &sv, &m, &sws);
     if (rc == BWTK_EWORKSPACE) {
         set_error("strict scan: %lld candidate runs exceed the workspace capacity %lld", (long long)m, (long long)ccap);
         return rc;
@@ -1299,8 +1480,12 @@ extern "C" int32_t bwtk_tier1_scan(const uint8_t *d_text, int64_t n, int32_t max
     bool by_runs = false;
     if (min_copies >= 2 && mmax >= 1) {
         int64_t nruns = 0;
+        // a one-symbol motif has entropy 0: with a positive entropy floor a homopolymer array is only ever
+        // emitted from 10 copies on (bwt.py:1499-1508), i.e. from runs of 9 -- which spares the list the
+        // ~5 % of all positions that start a run of 2..8
+        const int64_t min_run_u1 = min_entropy > 0.0 ? 9 : 0;
         int rc = strict::collect_runs(d_text, n, 1, mmax, min_copies, rkey0, rkey1, rval0, rval1, d_runcount, ccap,
-                                      pw.rws, st, &rk, &rv, &nruns);
+                                      pw.rws, st, &rk, &rv, &nruns, &pw.sws, min_run_u1);
         if (rc && rc != BWTK_EWORKSPACE) return rc;
         if (rc == BWTK_OK) {
             by_runs = true;

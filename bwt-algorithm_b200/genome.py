@@ -97,6 +97,15 @@ class GenomeScanner:
         self.used = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.profile_phases = False     # record events around the index build and every detector
+        self._phase_events = []
+        self.phase_ms: Dict[str, float] = {}
+
+    def _mark(self, name: str) -> None:
+        if self.profile_phases:
+            ev = self.torch.cuda.Event(enable_timing=True)
+            ev.record(self.main)
+            self._phase_events.append((name, ev))
 
     # ------------------------------------------------------------------ one contig
     def _rows_call(self, what: str, call) -> int:
@@ -113,6 +122,7 @@ class GenomeScanner:
     def _process(self, d_text, n: int, res: ContigRows) -> None:
         """Index build + the four detectors for one device-resident contig, on ``self.main``."""
         L, st = self.L, self.main.cuda_stream
+        self._mark("start")
         for _attempt in range(2):
             rc = L.bwtk_index_build(d_text.data_ptr(), n, self.occ_rate, self.sa.data_ptr(), None,
                                     self.bwt.data_ptr(), self.occ.data_ptr(), self.occ_rows, self.lcp.data_ptr(),
@@ -126,6 +136,7 @@ class GenomeScanner:
                 continue
             break
         _lib.check(rc, "index_build")
+        self._mark("index")
         res.sa_stats = self.stats.copy()
         wsp, wsb = self.ws.data_ptr(), self.ws.numel()
         n_seq = n - 1                      # callers append exactly one '$' (bwt.py:3053)
@@ -137,6 +148,7 @@ class GenomeScanner:
                 rec, cap, cnt, self.seen.data_ptr() if want_mask else None, wsp, wsb, st))
             res.span["tier1"] = (first, c)
             self.used += c
+            self._mark("tier1")
         if "strict" in self.kinds:
             first = self.used
             unit_cap = max(self.max_unit_len, min(n_seq // self.min_copies, 1000))   # bwt.py:3088-3096
@@ -144,6 +156,7 @@ class GenomeScanner:
                 d_text.data_ptr(), n, 1, unit_cap, 0, self.min_copies, rec, cap, cnt, wsp, wsb, st))
             res.span["strict"] = (first, c)
             self.used += c
+            self._mark("strict")
         if "plateaus" in self.kinds:
             first = self.used
             thr = C.c_int64(-1)
@@ -153,6 +166,7 @@ class GenomeScanner:
             res.span["plateaus"] = (first, c)
             res.threshold = int(thr.value)
             self.used += c
+            self._mark("plateaus")
         if "period" in self.kinds:
             first = self.used
             it = C.c_int64(0)
@@ -163,6 +177,7 @@ class GenomeScanner:
             res.span["period"] = (first, c)
             res.period_iterations = int(it.value)
             self.used += c
+            self._mark("period")
 
     # ------------------------------------------------------------------ a list of contigs
     def scan(self, contigs: Sequence, ids: Optional[Sequence[int]] = None, download: bool = True) -> List[ContigRows]:
@@ -178,6 +193,7 @@ class GenomeScanner:
         out: List[ContigRows] = []
         self.used = 0
         self.h2d_bytes = self.d2h_bytes = 0
+        self._phase_events = []
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream()
             self.main.wait_stream(cur)
@@ -229,6 +245,11 @@ class GenomeScanner:
             self.t_end.synchronize()
             cur.wait_stream(self.main)
             self.elapsed_ms = self.t_start.elapsed_time(self.t_end)
+            if self.profile_phases:
+                self.phase_ms = {}
+                for (_, a), (name, b) in zip(self._phase_events, self._phase_events[1:]):
+                    if name != "start":
+                        self.phase_ms[name] = self.phase_ms.get(name, 0.0) + a.elapsed_time(b)
         return out
 
     # ------------------------------------------------------------------ views

@@ -221,3 +221,36 @@ def test_tier1_and_period_scan_at_regime_boundaries(detect, oracle, n):
         want_m, it_m = oracle.period_scan(text, tier1_mask=m)
         got_m, git_m = detect.period_scan_rows(text, tier1_mask=m)
         assert git_m == it_m and np.array_equal(got_m, want_m), f"n={len(text)}: masked period scan differs"
+
+
+def test_strict_and_tier1_on_an_unaligned_text_view(oracle):
+    """The ordered small-unit run finder needs 16-byte aligned text; a view that starts at an odd address
+    takes the per-position kernel + sort instead.  Both must give the oracle's rows."""
+    import torch
+
+    from bwt_algorithm_b200 import detect
+
+    text = gen_contig(120_000, 11).tobytes() + b"$"
+    buf = torch.zeros(len(text) + 64, dtype=torch.uint8, device="cuda")
+    for off in (0, 1, 7, 16):
+        view = buf[off:off + len(text)]
+        view.copy_(torch.from_numpy(np.frombuffer(text, np.uint8).copy()))
+        assert view.data_ptr() % 16 == (buf.data_ptr() + off) % 16
+        rows = detect.strict_rows(view, 1, 1000, 0, 3)
+        assert np.array_equal(rows, oracle.strict_scan(text, 1, 1000, 0, 3)), f"strict rows differ at offset {off}"
+        t1 = detect.tier1_rows(view)
+        assert np.array_equal(t1, oracle.tier1_scan(text)), f"tier 1 rows differ at offset {off}"
+
+
+def test_tier1_homopolymer_floor_only_with_positive_entropy(oracle):
+    """min_entropy = 0 keeps short homopolymer arrays (the run list then holds every run of >= 2)."""
+    from bwt_algorithm_b200 import detect
+
+    rng = np.random.default_rng(5)
+    s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 60_000)].copy()
+    for k in range(40):
+        s[1000 * k + 10:1000 * k + 10 + 3 + k % 12] = ord("ACGT"[k % 4])
+    text = s.tobytes() + b"$"
+    for ent in (0.0, 0.5, 1.0):
+        got = detect.tier1_rows(text, 9, 3, 6, ent)
+        assert np.array_equal(got, oracle.tier1_scan(text, 9, 3, 6, ent)), f"min_entropy={ent}"
