@@ -34,6 +34,7 @@ from .motifs import MotifUtils
 from .records import TandemRepeat
 
 FAST_K1 = True     # tests switch it off to compare with the generic merge path
+STATS = {"requeued": 0}   # settled homopolymer events that a merge chain reached after all (tests look at it)
 
 _AT = np.zeros(256, np.int8)
 _AT[:] = -1                      # canonical class of a 1-bp motif: A/T -> 0, C/G -> 1, anything else: ask MotifUtils
@@ -161,9 +162,21 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
     free_from = 0
     mc1 = max(1, min_copies)
     seq_arr = text_arr[:seq_len]
-    for e in np.flatnonzero(todo).tolist():
-        if e < free_from:
-            continue
+    cands = np.flatnonzero(todo).tolist()
+    p_c, n_c = 0, len(cands)
+    pending = -1            # a settled event that a chain reached and undid: it is a candidate again, and the next one
+    while True:
+        while p_c < n_c and cands[p_c] < free_from:
+            p_c += 1
+        if pending >= 0 and (p_c >= n_c or pending <= cands[p_c]):
+            e, pending = pending, -1
+            if e < free_from:
+                continue
+        elif p_c < n_c:
+            e = cands[p_c]
+            p_c += 1
+        else:
+            break
         if fast_k1 and K[e] == 1 and _AT[seq_arr[S[e]]] >= 0:
             s0 = int(S[e])
             cls = int(_AT[seq_arr[s0]])
@@ -203,7 +216,9 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
                 else:
                     free_from = e + 1
                 if j < m and vrun[j] == 0 and link[j] and not todo[j]:
-                    return _finish_rows_slow(finder, chrom, text_arr, rows)     # an undone event is current again
+                    pending = j                  # an undone event is current again
+                    todo[j] = True
+                    STATS["requeued"] += 1
                 continue
             # fall through: redo this candidate on records (rows released above stay released)
         cur = make_row(e)
@@ -230,7 +245,9 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
         else:
             free_from = e + 1
         if j < m and vrun[j] == 0 and link[j] and not todo[j]:
-            return _finish_rows_slow(finder, chrom, text_arr, rows)             # an undone event is current again
+            pending = j                          # an undone event is current again
+            todo[j] = True
+            STATS["requeued"] += 1
 
     # ---- 4. refine (records with mismatches only; rows and virtual items are exact) + stable sort by (start, end)
     rec_list: List[TandemRepeat] = []

@@ -385,3 +385,29 @@ def test_row_chain_homopolymer_shortcut_equals_generic_path():
             assert [dataclasses.astuple(r) for r in fast[0]] == [dataclasses.astuple(r) for r in slow[0]], name
             total_events += len(slow[0])
     assert total_events > 1000
+
+
+def test_row_chain_requeues_an_undone_homopolymer_event():
+    """A merge chain that reaches a settled homopolymer event undoes it; the event's own link is then a candidate
+    again.  finish_rows picks it up next (it used to redo the whole contig on records, 8 s per chr21-sized contig).
+    Rows: the oracle's strict scan of A-rich text, three seeds that each hit the case once."""
+    import dataclasses
+
+    from bwt_algorithm_b200 import pipeline, rowchain
+    from oracle import oracle as orc
+
+    cfg = {"sa_sample_rate": 32, "show_progress": False, "allow_mismatches": True, "max_motif_length": 9,
+           "min_period": 10, "max_period": 1000, "min_copies": 3, "min_entropy": 1.0, "max_unit_len": 120}
+    hits = 0
+    for seed in (1, 3, 5):
+        rng = np.random.default_rng(seed)
+        seq = np.frombuffer(b"AAAT", np.uint8)[rng.integers(0, 4, 30_000)].tobytes().decode()
+        text = np.frombuffer((seq + "$").encode(), np.uint8)
+        rows = orc.strict_scan(text.tobytes(), 1, 12, 0, 3)
+        rowchain.STATS["requeued"] = 0
+        fast = rowchain.finish_rows(pipeline._contig_finder("c1", seq, cfg, "", ""), "c1", text, rows)
+        hits += rowchain.STATS["requeued"]
+        slow = rowchain._finish_rows_slow(pipeline._contig_finder("c1", seq, cfg, "", ""), "c1", text, rows)
+        assert fast[1:] == slow[1:]
+        assert [dataclasses.astuple(r) for r in fast[0]] == [dataclasses.astuple(r) for r in slow[0]]
+    assert hits >= 3
