@@ -263,18 +263,27 @@ def fm_section(torch, L, lib, dev, n, bwt, occ, ncp, totals, row, flush, args):
 
     ms = timed(run_batch)
     found = int((sp >= 0).sum().item())
-    sect = 2 * 10          # two ranks per character, one 64-B block (two 32-B sectors, one line) each
+    ktab = int(rep.ftab_k or 0)          # patterns start from the interval of their last ktab characters
+    sect = 2 * (10 - ktab)               # two ranks per remaining character, one 64-B block (two 32-B sectors) each
+    bytes_q = sect * 64 + (8 if ktab else 0) + 10 + 8
     peak, _ = measured_peak()
     out["random_10mers"] = {"queries": nq, "ms": round(ms, 4), "queries_per_s": round(nq / (ms * 1e-3), 1),
-                            "found": found,
+                            "found": found, "kmer_table": ktab,
                             "roofline": {"bound": "hbm-sectors", "unit": "GB/s",
-                                         "blocks_per_query": sect, "bytes_per_query": sect * 64 + 10 + 8,
-                                         "achieved": round(nq * (sect * 64 + 18) / (ms * 1e-3) / 1e9, 1), "peak": peak,
-                                         "frac": round(nq * (sect * 64 + 18) / (ms * 1e-3) / 1e9 / peak, 4),
+                                         "blocks_per_query": sect, "bytes_per_query": bytes_q,
+                                         "achieved": round(nq * bytes_q / (ms * 1e-3) / 1e9, 1), "peak": peak,
+                                         "frac": round(nq * bytes_q / (ms * 1e-3) / 1e9 / peak, 4),
                                          "note": "packed index (62 MB of blocks for chr1) is L2-resident: frac may exceed 1; "
                                                  "see profiles/ for lts__t_sectors and the L2 hit rate"}}
     want_sp, want_ep = sp.clone(), ep.clone()
     variants = {}
+    fx = rep.ensure_packed()
+    fx.ftab_k = 0
+    vms = timed(run_batch, reps=2)
+    fx.ftab_k = ktab
+    variants["no_kmer_table"] = {"ms": round(vms, 4), "queries_per_s": round(nq / (vms * 1e-3), 1),
+                                 "same_answers": bool(torch.equal(sp, want_sp) and torch.equal(ep, want_ep)),
+                                 "note": "all 10 LF steps (20 rank blocks per query) through the packed index"}
     for name, attrs in (("thread_per_query", {"thread_per_query": True}), ("no_l2_window", {"l2_persist": False}),
                         ("byte_bwt_occ_rows", {"use_packed": False})):
         for k, v in attrs.items():
@@ -284,11 +293,6 @@ def fm_section(torch, L, lib, dev, n, bwt, occ, ncp, totals, row, flush, args):
         variants[name] = {"ms": round(vms, 4), "queries_per_s": round(nq / (vms * 1e-3), 1), "same_answers": same}
         for k in attrs:
             setattr(rep, k, getattr(type(rep), k))
-    rep.build_ftab(8)
-    vms = timed(run_batch, reps=2)
-    variants["kmer_table_8"] = {"ms": round(vms, 4), "queries_per_s": round(nq / (vms * 1e-3), 1),
-                                "same_answers": bool(torch.equal(sp, want_sp) and torch.equal(ep, want_ep)),
-                                "note": "patterns start from the interval of their last 8 characters (65 536-entry table): 2 LF steps"}
     out["random_10mers"]["variants"] = variants
     del pats, lens, sp, ep, want_sp, want_ep
     return out

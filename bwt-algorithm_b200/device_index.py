@@ -31,8 +31,9 @@ class _FMSearch:
     # ------------------------------------------------------------------ packed search index
     #: searches run over the 64-byte rank blocks (bwtk_fm_*); False = the byte BWT + Occ rows
     use_packed = True
-    #: length of the k-mer interval table that seeds longer patterns (0 = none)
-    ftab_k = 0
+    #: length of the k-mer interval table that seeds longer patterns (0 = none; None = 8 from 2^20 symbols on:
+    #: the 65 536 intervals are level 8 of the motif sweep, 0.1 ms to build, and save 8 of a pattern's LF steps)
+    ftab_k = None
     #: keep the rank blocks resident in L2 while a batch streams through
     l2_persist = True
     #: one thread per query instead of four lanes sharing every block load (kept for A/B measurements)
@@ -71,8 +72,9 @@ class _FMSearch:
         self._fm = fx
         self._fm_keep = (blocks, exc_pos, exc_by_code, code_off)      # the struct holds raw pointers
         self.packed_bytes = blocks.numel() + 8 * int(cnt.value)
-        if self.ftab_k:
-            self.build_ftab(self.ftab_k)
+        k = self.ftab_k if self.ftab_k is not None else (8 if n >= (1 << 20) else 0)
+        if k:
+            self.build_ftab(k)
         return fx
 
     def build_ftab(self, k: int):

@@ -56,7 +56,7 @@ class _Lane:
     """Device buffers, stream and host-side outputs of one contig in flight."""
 
     def __init__(self, torch, L, max_n: int, occ_rate: int, scratch_rows: int, dev):
-        self.text = torch.empty(max_n, dtype=torch.uint8, device=dev)
+        self.text = [torch.empty(max_n, dtype=torch.uint8, device=dev) for _ in range(2)]   # current + prefetched
         self.sa = torch.empty(max_n, dtype=torch.int32, device=dev)
         self.bwt = torch.empty(max_n, dtype=torch.uint8, device=dev)
         self.lcp = torch.empty(max_n, dtype=torch.int32, device=dev)
@@ -70,6 +70,10 @@ class _Lane:
         self.scratch = torch.empty((scratch_rows, REC_W), dtype=torch.int32, device=dev)
         self.scratch_rows = scratch_rows
         self.stream = torch.cuda.Stream(device=dev)
+        self.dl = torch.cuda.Stream(device=dev)      # row downloads: the lane goes on computing meanwhile
+        self.up = torch.cuda.Stream(device=dev)      # text uploads: the lane's next contig arrives during this one
+        self.rows_ready = torch.cuda.Event()
+        self.up_done = [torch.cuda.Event() for _ in range(2)]
         self.totals = np.zeros(256, np.int64)
         self.row = np.full(256, -1, np.int32)
         self.stats = np.zeros(8, np.int64)
@@ -223,21 +227,35 @@ class GenomeScanner:
         torch = self.torch
         try:
             with torch.cuda.device(self.device), torch.cuda.stream(lane.stream):
-                while not errors:
+                def claim(slot: int):
+                    """Takes the next contig off the queue and starts its upload into text slot `slot`."""
                     with self._lock:
-                        if not queue:
-                            break
-                        i = queue.pop(0)
-                    t = contigs[i]
+                        if not queue or errors:
+                            return None
+                        j = queue.pop(0)
+                    t = contigs[j]
                     n = int(t.numel())
                     if n < 1 or n > self.max_n:
                         raise _lib.BwtkError(f"contig of {n} symbols does not fit the scanner (max_n={self.max_n})")
                     if t.is_cuda:
-                        d_text = t
-                    else:
-                        d_text = lane.text[:n]
-                        d_text.copy_(t, non_blocking=True)
-                        lane.h2d += n
+                        return j, t, n
+                    d = lane.text[slot][:n]
+                    with torch.cuda.stream(lane.up):
+                        d.copy_(t, non_blocking=True)
+                        lane.up_done[slot].record(lane.up)
+                    lane.h2d += n
+                    return j, d, n
+
+                slot = 0
+                nxt = claim(slot)
+                while nxt is not None and not errors:
+                    i, d_text, n = nxt
+                    if not contigs[i].is_cuda:
+                        lane.stream.wait_event(lane.up_done[slot])
+                    # the other slot's contig finished on this stream before the host got here (the detector
+                    # calls synchronise it): its text can be overwritten by the next upload
+                    slot ^= 1
+                    nxt = claim(slot)
                     res = ContigRows(contig=ids[i], n=n)
                     local = self._process(lane, d_text, n, res)
                     total = sum(c for _, c in local.values())
@@ -253,9 +271,14 @@ class GenomeScanner:
                     if total:
                         self.arena[first:first + total].copy_(lane.scratch[:total], non_blocking=True)
                         if download:
-                            self.host[first:first + total].copy_(self.arena[first:first + total], non_blocking=True)
+                            lane.rows_ready.record(lane.stream)
+                            with torch.cuda.stream(lane.dl):
+                                lane.dl.wait_event(lane.rows_ready)
+                                self.host[first:first + total].copy_(self.arena[first:first + total], non_blocking=True)
                             lane.d2h += total * REC_W * 4
                     out[i] = res
+                lane.stream.wait_stream(lane.dl)
+                lane.stream.wait_stream(lane.up)
                 lane.stream.synchronize()
         except BaseException as exc:   # noqa: BLE001 -- re-raised by scan() on the caller's thread
             errors.append(exc)
@@ -284,6 +307,8 @@ class GenomeScanner:
             active = self.lanes[: max(1, min(len(self.lanes), len(contigs)))]
             for lane in active:
                 lane.stream.wait_event(self.t_start)
+                lane.dl.wait_event(self.t_start)
+                lane.up.wait_event(self.t_start)
             if len(active) == 1:
                 self._lane_loop(active[0], contigs, ids, out, queue, download, errors)
             else:
