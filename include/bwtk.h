@@ -95,7 +95,11 @@ int32_t bwtk_byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals,
  * suffix array under byte order, shorter suffix first (key2 = -1 rule).
  * d_isa_out may be NULL; otherwise receives the inverse suffix array.
  * h_stats (may be NULL) receives int64[8]: rounds, bits/symbol, symbols/key,
- * active after round 0, sum of active over rounds, radix passes, 0, 0.
+ * active after round 0, sum of active over rounds, radix passes, path flags, 0.
+ * Path flags: bit 0 = ACGT$ 2-bit layout, bit 1 = round 0 by the MSD bucket sort
+ * (2-bit texts from 2^21 symbols on; environment BWTK_MSD=0 keeps the LSD sort,
+ * BWTK_MSD_MIN_N=<n> moves the threshold), bit 2 = first regroup pass fused into it
+ * (BWTK_MSD_FUSE=0 switches the fusion off).  The suffix array does not depend on the path.
  * Synchronises the stream (one 4-byte read-back per doubling round). */
 int64_t bwtk_sa_workspace_bytes(int64_t n);
 int32_t bwtk_sa_build(const uint8_t *d_text, int64_t n, int32_t *d_sa, int32_t *d_isa_out,

@@ -13,7 +13,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-SHORT = [("onesweep_kernel<unsigned int, bwtk::rsort::PackedSuffixSource", "onesweep_u32_gen"),
+SHORT = [("bucket_sort_kernel<(bool)1>", "bucket_sort_regroup"), ("bucket_sort_kernel<true>", "bucket_sort_regroup"),
+         ("bucket_sort_kernel<(bool)0>", "bucket_sort"), ("bucket_sort_kernel<false>", "bucket_sort"),
+         ("onesweep_kernel<unsigned int, bwtk::rsort::PackedSuffixSource", "onesweep_u32_gen"),
          ("onesweep_kernel<unsigned int, rsort::PackedSuffixSource", "onesweep_u32_gen"),
          ("onesweep_kernel<unsigned int, PackedSuffixSource", "onesweep_u32_gen"),
          ("onesweep_kernel<unsigned int", "onesweep_u32"), ("onesweep_kernel<unsigned long", "onesweep_u64"),
