@@ -339,7 +339,7 @@ def run_ours(args):
     my_bases = sum(lengths[i] for i in mine)
     max_n = max([lengths[i] for i in mine] + [2000]) + 1
     arena_rows = my_bases // 14 + 262144 * max(len(mine), 1)   # small contigs: the period scan's raw rows dominate
-    scanner = GenomeScanner(max_n, arena_rows, device=dev)
+    scanner = GenomeScanner(max_n, arena_rows, device=dev, lanes=args.lanes)
     all_rows_cap = total_bases // 14 + 262144 * len(lengths)
     gather_buf = torch.empty((all_rows_cap, 8), dtype=torch.int32, device=dev) if (rank == 0 and world > 1) else None
     kind_id = {k: j for j, k in enumerate(KINDS)}
@@ -552,7 +552,7 @@ def run_ours(args):
                        "generator": "SURVEY Appendix B density, vectorised on the device, seed 1000+i; parked in pinned host memory",
                        "detectors": "tier1(9,3,6,1.0) strict(u 1..1000, mm 0, copies 3) lcp_plateaus(1,1000,3) "
                                     "period_scan(1..1000, masked by Tier 1)",
-                       "occ_rate": 128, "l2": "inputs larger than L2: every contig touches >= 2 GB (no flush between genome steps)",
+                       "occ_rate": 128, "contigs_in_flight_per_gpu": args.lanes, "l2": "inputs larger than L2: every contig touches >= 2 GB (no flush between genome steps)",
                        "parallelism": f"contigs dealt to {world} rank(s) by LPT bin packing; rows gathered to rank 0 over NCCL",
                        "per_rank_bases": [int(float(x[7])) for x in allt]},
             "e2e": {"value": round(e2e_val, 4), "unit": "Gbases/s", "h2d_bytes_per_step": h2d_total,
@@ -752,6 +752,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every contig of the genome (smoke runs)")
     ap.add_argument("--fm-log2-queries", type=int, default=26, help="random 10-mers of the FM section (2^k)")
     ap.add_argument("--cpu-cores", type=int, default=64, help="upper bound on host processes of the CPU legs")
+    ap.add_argument("--lanes", type=int, default=2, help="contigs in flight per GPU (GenomeScanner lanes)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-window", type=int, default=REF_WINDOW,
                     help="bases per window (one per core and step) of the reference arm")

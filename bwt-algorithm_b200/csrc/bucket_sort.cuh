@@ -52,6 +52,7 @@ constexpr int SORT_ITEMS = CAP / SORT_THREADS;  // 16
 #define BWTK_MSD_BIN_PEER 32
 #endif
 constexpr int BIN_PEER = BWTK_MSD_BIN_PEER;     // sub-buckets up to this size: every element counts its smaller peers
+constexpr int PREFETCH_AHEAD = 2 * 148 + 64;          // sort CTAs resident at a time (two per SM) and a few more
 constexpr int BIG_LIST = 256;                   // larger ones (at most CAP_EFF / (BIN_PEER + 1) < 256 of them): counting sort by the CTA
 static_assert(CAP_EFF / (BIN_PEER + 1) < BIG_LIST, "big-bin list");
 constexpr int CA_THREADS = 512;
@@ -466,6 +467,16 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
     const int LB = 32 - nb_bits, DS = LB - SUB_BITS;
     const uint32_t prefix = b << LB;
     const bool sorted_here = cnt > 0 && cnt <= (uint32_t)CAP_EFF;
+    {
+        // the pairs of the bucket that will run when the CTAs now resident are done: into L2 ahead of time
+        const uint32_t pb = b + PREFETCH_AHEAD;
+        if (pb < (1u << nb_bits)) {
+            const uint32_t p0 = __ldg(bstart + pb), p1 = __ldg(bstart + pb + 1);
+            const uint32_t lines = (p1 - p0 + 15u) / 16u;                 // 128-byte lines of 16 pairs
+            if ((uint32_t)tid < lines && lines <= (uint32_t)SORT_THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pairs + p0 + (uint32_t)tid * 16u));
+        }
+    }
 
     if (sorted_here) {
         uint32_t e[SORT_ITEMS];
@@ -542,9 +553,17 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
             const uint32_t x = s_b[r];
             const uint32_t d = x >> (IDX_BITS + DS);
             const uint32_t lo = s_h[d], hi = s_h[d + 1];
-            if (hi - lo <= (uint32_t)BIN_PEER) {
+            const uint32_t sz = hi - lo;
+            if (sz <= 4u) {
+                // the common case (mean sub-bucket: 1.4 elements) without a loop; s_b has a readable tail
+                const uint32_t a0 = s_b[lo], a1 = s_b[lo + 1], a2 = s_b[lo + 2], a3 = s_b[lo + 3];
+                uint32_t f = lo + (a0 < x ? 1u : 0u);
+                f += (sz > 1u && a1 < x) ? 1u : 0u;
+                f += (sz > 2u && a2 < x) ? 1u : 0u;
+                f += (sz > 3u && a3 < x) ? 1u : 0u;
+                s_a[f] = x;
+            } else if (sz <= (uint32_t)BIN_PEER) {
                 uint32_t f = lo;
-#pragma unroll 4
                 for (uint32_t j = lo; j < hi; j++) f += s_b[j] < x ? 1u : 0u;
                 s_a[f] = x;
             }
@@ -626,36 +645,47 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
     uint32_t n_active = 0;
     if (sorted_here) {
         const int words = (int)((cnt + 31) >> 5);
-        // head / active flags: element j is a head when its key differs from its predecessor's or either of
-        // them is a short suffix; it is active unless it and its successor are both heads
+        // head flags: element j is a head when its key differs from its predecessor's or either of them is a
+        // short suffix (slots past the end count as heads: the bucket's last element is followed by one);
+        // the same compare finds where the 16-bit key prefix changes (prefix table, < 16 bucket bits only)
+        const int psub = 16 - nb_bits;
         for (uint32_t j0 = warp * 32; j0 < cnt; j0 += SORT_THREADS) {
             const uint32_t j = j0 + lane;
-            bool head = true, nhead = true;
+            bool head = true;
             if (j < cnt) {
                 const uint32_t x = s_a[j];
-                const bool xs = (x & (CAP - 1)) < (uint32_t)SHORT_SLOTS;
-                if (j > 0) {
-                    const uint32_t p = s_a[j - 1];
-                    head = (p >> IDX_BITS) != (x >> IDX_BITS) || xs || (p & (CAP - 1)) < (uint32_t)SHORT_SLOTS;
-                }
-                if (j + 1 < cnt) {
-                    const uint32_t q = s_a[j + 1];
-                    nhead = (q >> IDX_BITS) != (x >> IDX_BITS) || xs || (q & (CAP - 1)) < (uint32_t)SHORT_SLOTS;
+                const uint32_t p = j > 0 ? s_a[j - 1] : ~x;
+                head = j == 0 || (p >> IDX_BITS) != (x >> IDX_BITS) || (x & (CAP - 1)) < (uint32_t)SHORT_SLOTS ||
+                       (p & (CAP - 1)) < (uint32_t)SHORT_SLOTS;
+                if (psub > 0) {
+                    const int32_t lp = (int32_t)((x >> IDX_BITS) >> (LB - psub));
+                    const int32_t pp = j > 0 ? (int32_t)((p >> IDX_BITS) >> (LB - psub)) : -1;
+                    for (int32_t q = pp + 1; q <= lp; q++) rg.ptab[(b << psub) + q] = (int32_t)(b0 + j);
+                    if (j + 1 == cnt)
+                        for (int32_t q = lp + 1; q < (1 << psub); q++) rg.ptab[(b << psub) + q] = (int32_t)(b0 + cnt);
                 }
             }
-            const unsigned hb = __ballot_sync(0xffffffffu, head && j < cnt);
-            const unsigned ab = __ballot_sync(0xffffffffu, j < cnt && !(head && nhead));
-            if (lane == 0) { s_hb[j0 >> 5] = hb; s_ab[j0 >> 5] = ab; }
+            const unsigned hb = __ballot_sync(0xffffffffu, head);
+            if (lane == 0) s_hb[j0 >> 5] = hb;
         }
         __syncthreads();
-        // per-word carries: 256 words at most, 8 per lane of warp 0 (max-scan of heads, sum-scan of actives)
+        // per-word carries: 256 words at most, 8 per lane of warp 0 (max-scan of heads, sum-scan of actives);
+        // an element is active unless it and its successor are both heads
         if (warp == 0) {
             uint32_t lh[8], la[8];
             uint32_t mh = 0, sa_ = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int w = lane * 8 + k;
-                const uint32_t hbw = w < words ? s_hb[w] : 0u, abw = w < words ? s_ab[w] : 0u;
+                uint32_t hbw = 0u, abw = 0u;
+                if (w < words) {
+                    hbw = s_hb[w];
+                    const uint32_t nxt = w + 1 < words ? s_hb[w + 1] : 0xffffffffu;
+                    const uint32_t valid = (uint32_t)(w + 1) * 32u <= cnt ? 0xffffffffu : ((1u << (cnt & 31u)) - 1u);
+                    abw = ~(hbw & ((hbw >> 1) | (nxt << 31))) & valid;
+                    s_ab[w] = abw;
+                    hbw &= valid;
+                }
                 lh[k] = hbw ? (uint32_t)(w * 32 + 31 - __clz(hbw)) + 1u : 0u;   // last head in the word (+1), 0: none
                 la[k] = (uint32_t)__popc(abw);
                 mh = lh[k] > mh ? lh[k] : mh;
@@ -690,20 +720,11 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
     volatile unsigned long long *lb_st = rg.status;
     const unsigned long long F_AGG = 1ull << 62, F_INCL = 2ull << 62;
     if (tid == 0) lb_st[b] = (b == 0 ? F_INCL : F_AGG) | n_active;
-    // 16-bit prefix table: entries of this bucket's key range (fewer than 16 bucket bits only)
-    if (nb_bits < 16 && cnt <= (uint32_t)CAP_EFF) {
-        const int sub = 16 - nb_bits;                       // 1..3 extra bits
-        const uint32_t base = b << sub, per = 1u << sub;
-        if (!sorted_here) {
-            // empty bucket: all its prefixes start where the bucket would
-            for (uint32_t q = tid; q < per; q += SORT_THREADS) rg.ptab[base + q] = (int32_t)b0;
-        } else {
-            for (uint32_t j = tid; j <= cnt; j += SORT_THREADS) {
-                const int32_t lp = j < cnt ? (int32_t)((s_a[j] >> IDX_BITS) >> (LB - sub)) : (int32_t)per;
-                const int32_t pp = j > 0 ? (int32_t)((s_a[j - 1] >> IDX_BITS) >> (LB - sub)) : -1;
-                for (int32_t q = pp + 1; q <= lp && q < (int32_t)per; q++) rg.ptab[base + q] = (int32_t)(b0 + j);
-            }
-        }
+    // 16-bit prefix table (fewer than 16 bucket bits only): an empty bucket's prefixes all start where the bucket would
+    // (sorted buckets wrote theirs with the head flags, oversize ones do in ovf_regroup_kernel)
+    if (nb_bits < 16 && cnt == 0) {
+        const int sub = 16 - nb_bits;
+        for (uint32_t q = tid; q < (1u << sub); q += SORT_THREADS) rg.ptab[(b << sub) + q] = (int32_t)b0;
     }
     if (nb_bits < 16 && b + 1 == (1u << nb_bits) && tid == 0) rg.ptab[65536] = (int32_t)n;
     if (sorted_here) {

@@ -13,7 +13,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-SHORT = [("bucket_sort_kernel<(bool)1>", "bucket_sort_regroup"), ("bucket_sort_kernel<true>", "bucket_sort_regroup"),
+SHORT = [("bucket_sort_kernel<1>", "bucket_sort_regroup"), ("bucket_sort_kernel<0>", "bucket_sort"),
+         ("bucket_sort_kernel<(bool)1>", "bucket_sort_regroup"), ("bucket_sort_kernel<true>", "bucket_sort_regroup"),
          ("bucket_sort_kernel<(bool)0>", "bucket_sort"), ("bucket_sort_kernel<false>", "bucket_sort"),
          ("onesweep_kernel<unsigned int, bwtk::rsort::PackedSuffixSource", "onesweep_u32_gen"),
          ("onesweep_kernel<unsigned int, rsort::PackedSuffixSource", "onesweep_u32_gen"),
