@@ -967,13 +967,28 @@ __global__ void coarse_walk_kernel(const int32_t *__restrict__ jbig, const int32
     *nanchor = a;
 }
 
-__global__ void fine_walk_kernel(const int32_t *__restrict__ succ, const int32_t *__restrict__ anchor,
-                                 const unsigned *__restrict__ nanchor, int64_t hops, uint8_t *__restrict__ onpath)
+// second level: from every coarse anchor, 2^kappa jumps of 2^kappa hops each -> anchor2[a << kappa | j] (-1: none)
+__global__ void mid_walk_kernel(const int32_t *__restrict__ jmid, const int32_t *__restrict__ anchor,
+                                const unsigned *__restrict__ nanchor, int kappa, int32_t *__restrict__ anchor2)
 {
     int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= (int64_t)*nanchor) return;
     int32_t v = anchor[a];
-    for (int64_t h = 0; h < hops && v >= 0; h++) {
+    int32_t *dst = anchor2 + (a << kappa);
+    for (int64_t j = 0; j < (1ll << kappa); j++) {
+        dst[j] = v;
+        if (v >= 0) v = jmid[v];
+    }
+}
+
+// third level: 2^kappa single hops from every second-level anchor, marking the path
+__global__ void fine_walk_kernel(const int32_t *__restrict__ succ, const int32_t *__restrict__ anchor2,
+                                 const unsigned *__restrict__ nanchor, int kappa, uint8_t *__restrict__ onpath)
+{
+    int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= ((int64_t)*nanchor << kappa)) return;
+    int32_t v = anchor2[a];
+    for (int64_t h = 0; h < (1ll << kappa) && v >= 0; h++) {
         onpath[v] = 1;
         v = succ[v];
     }
@@ -1018,7 +1033,7 @@ struct Tier1Writer {
 
 // scratch shared by the passes of one call
 struct PassWs {
-    int32_t *cpos, *cend, *succ, *j0, *j1, *anchor;
+    int32_t *cpos, *cend, *succ, *j0, *j1, *j2, *anchor, *anchor2;
     uint32_t *cidx0, *cidx1;
     unsigned long long *ckey0, *ckey1;
     uint8_t *onpath;
@@ -1030,7 +1045,7 @@ struct PassWs {
 
 static int64_t pass_ws_bytes(int64_t n)
 {
-    return 8 * align_up(n * 4, 256) + 2 * align_up(n * 8, 256) + align_up(n, 256) + rsort::workspace_bytes(n) +
+    return 10 * align_up(n * 4, 256) + align_up(n * 4 + 4096, 256) + 2 * align_up(n * 8, 256) + align_up(n, 256) + rsort::workspace_bytes(n) +
            scan::workspace_bytes(n) + 4096;
 }
 
@@ -1039,8 +1054,8 @@ static PassWs carve_pass_ws(Carver &c, int64_t n)
     PassWs w;
     w.cpos = c.take<int32_t>(n); w.cend = c.take<int32_t>(n);
     w.cidx0 = c.take<uint32_t>(n); w.cidx1 = c.take<uint32_t>(n);
-    w.succ = c.take<int32_t>(n); w.j0 = c.take<int32_t>(n); w.j1 = c.take<int32_t>(n);
-    w.anchor = c.take<int32_t>(n);
+    w.succ = c.take<int32_t>(n); w.j0 = c.take<int32_t>(n); w.j1 = c.take<int32_t>(n); w.j2 = c.take<int32_t>(n);
+    w.anchor = c.take<int32_t>(n); w.anchor2 = c.take<int32_t>(2 * n + 1024);
     w.ckey0 = c.take<unsigned long long>(n); w.ckey1 = c.take<unsigned long long>(n);
     w.onpath = c.take<uint8_t>(n);
     w.rws = rsort::carve(c, n);
@@ -1078,25 +1093,32 @@ static int greedy_replay(int64_t K, int64_t path_bound, int64_t limit, int64_t s
     succ_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(w.cend, skey, sidx, K, step, abits, limit, w.succ,
                                                           w.d_first);
     BWTK_LAUNCH_CHECK();
-    // jump table for 2^kappa hops, kappa ~ log2(path length)/2: the coarse walk (one thread) then
-    // takes ~sqrt(path) jumps and every fine walk ~sqrt(path) hops
+    // Three-level walk along the visited path (at most `plen` candidates): jump tables for 2^kappa and 4^kappa
+    // hops, kappa ~ log2(plen)/3.  One thread takes plen/4^kappa coarse jumps, then a thread per coarse anchor
+    // 2^kappa middle jumps, then a thread per middle anchor 2^kappa single hops -- ~3 plen^(1/3) dependent loads
+    // in a row instead of the 2 sqrt(plen) of a two-level walk (a pass over a chromosome has millions of runs).
     const int64_t plen = path_bound > 0 && path_bound < K ? path_bound : K;
-    int kappa = 0;
-    while ((1ll << (2 * kappa)) < plen) kappa++;
-    const int32_t *jbig = w.succ;
-    int32_t *ja = w.j0, *jb = w.j1;
-    for (int r = 0; r < kappa; r++) {
-        double_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(jbig, ja, K);
+    int kappa = 1;
+    while ((1ll << (3 * kappa)) < plen) kappa++;
+    const int32_t *cur = w.succ, *jmid = w.succ;
+    int32_t *bufs[3] = {w.j0, w.j1, w.j2};
+    for (int r = 0; r < 2 * kappa; r++) {
+        int32_t *dst = nullptr;
+        for (int q = 0; q < 3; q++)
+            if (bufs[q] != cur && bufs[q] != jmid) { dst = bufs[q]; break; }
+        double_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(cur, dst, K);
         BWTK_LAUNCH_CHECK();
-        jbig = ja;
-        int32_t *t = ja; ja = jb; jb = t;
+        cur = dst;
+        if (r == kappa - 1) jmid = cur;
     }
-    coarse_walk_kernel<<<1, 32, 0, st>>>(jbig, w.d_first, w.anchor, w.d_nanchor);
+    coarse_walk_kernel<<<1, 32, 0, st>>>(cur, w.d_first, w.anchor, w.d_nanchor);
     BWTK_LAUNCH_CHECK();
     BWTK_CUDA(bwtk::zero_async(w.onpath, (size_t)K, st));
-    int64_t max_anchor = (plen >> kappa) + 2;
-    fine_walk_kernel<<<(unsigned)ceil_div(max_anchor, 128), 128, 0, st>>>(w.succ, w.anchor, w.d_nanchor,
-                                                                        1ll << kappa, w.onpath);
+    const int64_t max_anchor = (plen >> (2 * kappa)) + 2;
+    mid_walk_kernel<<<(unsigned)ceil_div(max_anchor, 128), 128, 0, st>>>(jmid, w.anchor, w.d_nanchor, kappa, w.anchor2);
+    BWTK_LAUNCH_CHECK();
+    fine_walk_kernel<<<(unsigned)ceil_div(max_anchor << kappa, 128), 128, 0, st>>>(w.succ, w.anchor2, w.d_nanchor, kappa,
+                                                                                 w.onpath);
     BWTK_LAUNCH_CHECK();
     CountPath cp{w.onpath};
     EmitPath<Writer> ep{w.cpos, w.cend, writer, d_rec, rec_base, cap};
