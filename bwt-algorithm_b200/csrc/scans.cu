@@ -354,11 +354,9 @@ template <int U> struct SmallRuns {
             const unsigned long long K = 0x7f7f7f7f7f7f7f7full;
             x0 = ~(((x0 & K) + K) | x0 | K);
             x1 = ~(((x1 & K) + K) | x1 | K);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                e |= (uint32_t)((x0 >> (8 * j + 7)) & 1ull) << j;
-                e |= (uint32_t)((x1 >> (8 * j + 7)) & 1ull) << (8 + j);
-            }
+            // bit 7 of every byte -> one byte (the multiply adds the eight bits up in its top byte)
+            e = (uint32_t)(((x0 >> 7) * 0x0102040810204080ull) >> 56) |
+                ((uint32_t)(((x1 >> 7) * 0x0102040810204080ull) >> 56) << 8);
             if (p0 + 16 > lim) e &= lim > p0 ? ((1u << (int)(lim - p0)) - 1u) : 0u;
         } else {
             for (int j = 0; j < 16; j++) {
@@ -369,13 +367,10 @@ template <int U> struct SmallRuns {
         *prev = p0 > 0 && p0 - 1 < lim && __ldg(text + p0 - 1) == __ldg(text + p0 - 1 + U);
         return e;
     }
-    // calls f(start, end) for every maximal run of >= L matches that starts in the chunk
-    template <typename F> __device__ __forceinline__ void for_runs(int64_t c, F f) const
+    // calls f(start, end) for every maximal run of >= L matches that starts in the chunk with match mask e
+    template <typename F> __device__ __forceinline__ void for_runs(int64_t c, uint32_t e, bool prev, F f) const
     {
         const int64_t p0 = c * 16;
-        if (p0 >= n - U) return;
-        bool prev;
-        const uint32_t e = mask(p0, &prev);
         uint32_t starts = e & ~((e << 1) | (prev ? 1u : 0u)) & 0xffffu;
         const int64_t lim = n - U;
         while (starts) {
@@ -392,12 +387,25 @@ template <int U> struct SmallRuns {
         }
     }
 };
+// the match masks of a thread's chunks are computed once, in the count phase, and kept for the emit phase
+struct SmallRunsCtx {
+    uint32_t e[scan::ITEMS];
+    uint32_t prev;
+};
 template <int U> struct SmallRunsCount {
+    using Ctx = SmallRunsCtx;
     SmallRuns<U> sr;
-    __device__ unsigned long long operator()(int64_t c) const
+    __device__ unsigned long long operator()(int64_t c, int k, Ctx &ctx) const
     {
+        if (k == 0) ctx.prev = 0;
+        ctx.e[k] = 0;
+        if (c * 16 >= sr.n - U) return 0;
+        bool prev;
+        const uint32_t e = sr.mask(c * 16, &prev);
+        ctx.e[k] = e;
+        if (prev) ctx.prev |= 1u << k;
         unsigned cnt = 0;
-        sr.for_runs(c, [&](int64_t, int64_t) { cnt++; });
+        sr.for_runs(c, e, prev, [&](int64_t, int64_t) { cnt++; });
         return cnt;
     }
 };
@@ -405,11 +413,11 @@ template <int U> struct SmallRunsEmit {
     SmallRuns<U> sr;
     CandOut out;
     const unsigned long long *base;   // device: runs already in the list
-    __device__ void operator()(int64_t c, unsigned long long excl, unsigned long long cnt) const
+    __device__ void operator()(int64_t c, int k, unsigned long long excl, unsigned long long cnt, SmallRunsCtx &ctx) const
     {
         if (!cnt) return;
         unsigned long long at = *base + excl;
-        sr.for_runs(c, [&](int64_t a, int64_t b) {
+        sr.for_runs(c, ctx.e[k], (ctx.prev >> k) & 1u, [&](int64_t a, int64_t b) {
             if ((int64_t)at < out.cap) {
                 out.key[at] = ((unsigned long long)(out.umax - U) << out.abits) | (unsigned long long)a;
                 out.val[at] = (uint32_t)b;
