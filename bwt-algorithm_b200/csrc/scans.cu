@@ -1250,29 +1250,65 @@ __global__ void max_kernel(const int32_t *__restrict__ lcp, int64_t n, int *__re
     if ((threadIdx.x & 31) == 0) atomicMax(out, v);
 }
 
-// hi 31 bits: plateau starts, lo 31 bits: plateau members
+// hi 31 bits: plateau starts, lo 31 bits: plateau members.  One scan element = a chunk of 16 LCP values
+// (four 16-byte loads; the LCP array of an index build is 16-byte aligned): members are rare, and a scan
+// element per LCP value spent ten times the array's read time on per-element bookkeeping.
 struct CountMembers {
     const int32_t *lcp;
+    int64_t n;
     int thr;
-    __device__ uint64_t operator()(int64_t r) const
+    // bit j of *in: lcp[16c + j] >= thr; *prev: the same for lcp[16c - 1]
+    __device__ __forceinline__ void masks(int64_t c, uint32_t *in, bool *prev) const
     {
-        bool in = lcp[r] >= thr;
-        bool start = in && (r == 0 || lcp[r - 1] < thr);
-        return ((uint64_t)start << 31) | (uint64_t)in;
+        const int64_t r0 = c * 16;
+        uint32_t m = 0;
+        if (r0 + 16 <= n && (((uintptr_t)lcp) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(lcp + r0) + q);
+                m |= (uint32_t)(v.x >= thr) << (4 * q) | (uint32_t)(v.y >= thr) << (4 * q + 1) |
+                     (uint32_t)(v.z >= thr) << (4 * q + 2) | (uint32_t)(v.w >= thr) << (4 * q + 3);
+            }
+        } else {
+            for (int j = 0; j < 16 && r0 + j < n; j++) m |= (uint32_t)(lcp[r0 + j] >= thr) << j;
+        }
+        *in = m;
+        *prev = r0 > 0 && lcp[r0 - 1] >= thr;
+    }
+    __device__ uint64_t operator()(int64_t c) const
+    {
+        uint32_t in;
+        bool prev;
+        masks(c, &in, &prev);
+        const uint32_t starts = in & ~((in << 1) | (prev ? 1u : 0u));
+        return ((uint64_t)__popc(starts) << 31) | (uint64_t)__popc(in);
     }
 };
 struct EmitMembers {
+    CountMembers cm;
     const int32_t *sa;
     int abits;
     unsigned long long *key;  // (segment id << abits) | text position
     uint32_t *val;
-    __device__ void operator()(int64_t r, uint64_t excl, uint64_t cnt) const
+    __device__ void operator()(int64_t c, uint64_t excl, uint64_t cnt) const
     {
         if (!(cnt & 0x7fffffffull)) return;
-        uint64_t seg = (excl >> 31) + (cnt >> 31);  // starts up to and including r
+        uint32_t in;
+        bool prev;
+        cm.masks(c, &in, &prev);
+        uint64_t seg = excl >> 31;              // starts before this chunk
         uint64_t slot = excl & 0x7fffffffull;
-        key[slot] = (seg << abits) | (uint64_t)(uint32_t)sa[r];
-        val[slot] = 0;
+        bool was = prev;
+        for (int j = 0; j < 16; j++) {
+            const bool is = (in >> j) & 1u;
+            if (is) {
+                if (!was) seg++;                // starts up to and including this member
+                key[slot] = (seg << abits) | (uint64_t)(uint32_t)sa[c * 16 + j];
+                val[slot] = 0;
+                slot++;
+            }
+            was = is;
+        }
     }
 };
 
@@ -1616,9 +1652,9 @@ extern "C" int32_t bwtk_lcp_plateaus(const uint8_t *d_text, int64_t n_text, cons
         return BWTK_EINVAL;
     }
     const int abits = strict::bits_for(n_text > n ? n_text : n);
-    plateau::CountMembers cm{d_lcp, (int)thr};
-    plateau::EmitMembers em{d_sa, abits, key0, val0};
-    int rc = scan::run(n, cm, em, sws, st);
+    plateau::CountMembers cm{d_lcp, n, (int)thr};
+    plateau::EmitMembers em{cm, d_sa, abits, key0, val0};
+    int rc = scan::run(ceil_div(n, 16), cm, em, sws, st);
     if (rc) return rc;
     unsigned long long h_tot = 0;
     BWTK_CUDA(cudaMemcpyAsync(&h_tot, sws.total, 8, cudaMemcpyDeviceToHost, st));
