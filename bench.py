@@ -752,7 +752,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every contig of the genome (smoke runs)")
     ap.add_argument("--fm-log2-queries", type=int, default=26, help="random 10-mers of the FM section (2^k)")
     ap.add_argument("--cpu-cores", type=int, default=64, help="upper bound on host processes of the CPU legs")
-    ap.add_argument("--lanes", type=int, default=2, help="contigs in flight per GPU (GenomeScanner lanes)")
+    ap.add_argument("--lanes", type=int, default=4, help="contigs in flight per GPU (GenomeScanner lanes)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-window", type=int, default=REF_WINDOW,
                     help="bases per window (one per core and step) of the reference arm")

@@ -10,7 +10,8 @@ that unit for a rank that owns one B200 and a list of contigs:
         --bwtk_period_scan (a16, masked by the Tier 1 calls)--> int32[R, 8] rows in the lane's scratch
         --D2D--> the scanner's row arena --D2H--> pinned host arena (optional)
 
-``lanes`` contigs are in flight at once (default 2), each on its own host thread, CUDA stream and set of
+``lanes`` contigs are in flight at once (default 4; 70 bytes of device memory per symbol of the longest contig
+and lane), each on its own host thread, CUDA stream and set of
 device buffers: the suffix-sort rounds, the nine Tier 1 passes and the period scan are chains of small
 launches with host read-backs in between, and a second contig's kernels fill the SMs they leave idle
 (the C-ABI calls release the GIL and only ever synchronise the stream they are given).  The lanes take
@@ -88,7 +89,7 @@ class GenomeScanner:
     def __init__(self, max_n: int, arena_rows: int, device=None, occ_rate: int = 128, host_arena: bool = True,
                  kinds: Sequence[str] = KINDS, min_copies: int = 3, max_motif_len: int = 9,
                  min_array_len: int = 6, min_entropy: float = 1.0, max_period: int = 1000,
-                 max_unit_len: int = 120, allow_mismatches: bool = True, lanes: int = 2):
+                 max_unit_len: int = 120, allow_mismatches: bool = True, lanes: int = 4):
         torch = _lib.require_cuda()
         self.torch = torch
         self.L = L = _lib.lib()
