@@ -25,6 +25,7 @@ namespace bwtk {
 // ===========================================================================
 namespace strict {
 
+constexpr int MAX_DYN_SMEM = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 constexpr int TP = 8192;       // positions per CTA tile
 constexpr int THREADS = 256;   // 8 warps x 1024 positions
 
@@ -567,11 +568,12 @@ static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t 
         int64_t u_per_block = ceil_div(nu, ysplit);
         ysplit = ceil_div(nu, u_per_block);
         size_t smem = (size_t)(TP + byte_hi + 16);
-        static size_t smem_set = 0;
-        if (smem > 48 * 1024 && smem > smem_set) {
-            BWTK_CUDA(cudaFuncSetAttribute(find_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set = smem;
-        }
+        // the opt-in maximum once (thread-safe static initialisation: several contigs are scanned concurrently,
+        // and a per-call "raise if larger" would let a small contig's call lower the limit under a large one's)
+        static const cudaError_t attr_rc =
+            cudaFuncSetAttribute(find_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+        BWTK_CUDA(attr_rc);
+        BWTK_REQUIRE(smem <= (size_t)MAX_DYN_SMEM, "unit length too large for the run finder's shared-memory tile");
         dim3 grid((unsigned)tiles, (unsigned)ysplit);
         find_runs_kernel<<<grid, THREADS, smem, st>>>(d_text, n, big_lo, byte_hi, u_per_block, mc, out);
         BWTK_LAUNCH_CHECK();
@@ -587,11 +589,10 @@ static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t 
         ysplit = ceil_div(nu, u_per_block);
         const size_t span16 = (size_t)((TPK + u_hi + 2 * GK + 15) & ~15ll);
         size_t smem = span16 + span16 / 4 + 64;
-        static size_t smem16_set = 0;
-        if (smem > 48 * 1024 && smem > smem16_set) {
-            BWTK_CUDA(cudaFuncSetAttribute(find_runs16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem16_set = smem;
-        }
+        static const cudaError_t attr16_rc =
+            cudaFuncSetAttribute(find_runs16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+        BWTK_CUDA(attr16_rc);
+        BWTK_REQUIRE(smem <= (size_t)MAX_DYN_SMEM, "unit length too large for the run finder's shared-memory tile");
         dim3 grid((unsigned)tiles, (unsigned)ysplit);
         prof::Scope ps("find_runs16_kernel", n, st);
         find_runs16_kernel<<<grid, THREADS, smem, st>>>(d_text, n, pk_lo, u_hi, u_per_block, mc, out);
