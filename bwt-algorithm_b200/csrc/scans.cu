@@ -25,7 +25,7 @@ namespace bwtk {
 // ===========================================================================
 namespace strict {
 
-constexpr int MAX_DYN_SMEM = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+constexpr int MAX_DYN_SMEM = 160 * 1024;   // dynamic shared memory the run finders may ask for (units up to 60 000: 116 KB)
 constexpr int TP = 8192;       // positions per CTA tile
 constexpr int THREADS = 256;   // 8 warps x 1024 positions
 
