@@ -74,6 +74,9 @@ _SIGS = {
     "bwtk_tier1_scan": (_i32, [_p, _i64, _i32, _i32, _i32, C.c_double, _p, _i64, _p, _p, _p, _i64, _p]),
     "bwtk_strict_workspace_bytes": (_i64, [_i64, _i64]),
     "bwtk_strict_scan": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _i64, _p]),
+    "bwtk_repeat_hint_bytes": (_i64, [_i64]),
+    "bwtk_repeat_hint": (_i32, [_p, _p, _i64, _i32, _p, _p]),
+    "bwtk_strict_scan_hinted": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _i32, _p, _i64, _p]),
     "bwtk_plateau_workspace_bytes": (_i64, [_i64]),
     "bwtk_lcp_plateaus": (_i32, [_p, _i64, _p, _p, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _i64, _p]),
     "bwtk_extend_batch": (_i32, [_p, _i64, _p, _p, _p, _i64, _i32, _p, _p]),

@@ -309,6 +309,101 @@ __global__ void __launch_bounds__(THREADS)
         scan_units16<false>(text, s_text, n, t0, (int)ua, (int)ub, (int)mc, wbase, base, dirty, out);
 }
 
+// ---- the 16-position search restricted to groups whose 16-mer occurs more than once -----------------------
+// A group of 16 aligned positions p can only match its copy at p + u if the 16-mer at p occurs a second time in
+// the text, i.e. if suffix p shares >= 16 symbols with a neighbour in suffix order.  With the index at hand
+// (bwtk_repeat_hint: one pass over the LCP array sets a bit for both suffixes of every neighbouring pair with
+// LCP >= 16) only those groups -- 6 % on planted random sequence -- are compared at all: they are listed, and a
+// warp per listed group stages the group's next ~1000 bases as 2-bit codes in shared memory and tries every
+// unit length against them, 32 at a time.  Same runs as find_runs16_kernel (matches are re-checked on the bytes;
+// a run is reported by the first matching group of its streak), in any order.
+__global__ void __launch_bounds__(256)
+    hint_list_kernel(const uint32_t *__restrict__ hint, int64_t n, uint32_t *__restrict__ list, unsigned *__restrict__ count,
+                     unsigned cap)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // aligned group index
+    const int64_t p = g * GK;
+    bool on = false;
+    if (p + GK <= n) on = (__ldg(hint + (p >> 5)) >> (p & 31)) & 1u;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (bal == 0u) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (on) {
+        const unsigned at = base + (unsigned)__popc(bal & ((1u << lane) - 1u));
+        if (at < cap) list[at] = (uint32_t)p;
+    }
+}
+
+constexpr int HL_WARPS = 8;          // groups per CTA
+constexpr int HL_WORDS = 72;         // 2-bit words staged per group: 16 * 72 = 1152 positions >= 16 + 1000 + 16
+
+__global__ void __launch_bounds__(HL_WARPS * 32)
+    find_runs16_list_kernel(const uint8_t *__restrict__ text, int64_t n, const uint32_t *__restrict__ list,
+                            const unsigned *__restrict__ count, unsigned cap, int64_t u_lo, int64_t u_hi, int64_t mc,
+                            CandOut out)
+{
+    __shared__ uint32_t s_codes[HL_WARPS][HL_WORDS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned total = *count;
+    if (total > cap) total = cap;
+    uint32_t *codes = s_codes[warp];
+    for (unsigned gi = blockIdx.x * HL_WARPS + warp; gi < total; gi += gridDim.x * HL_WARPS) {
+        const int64_t p = list[gi];
+        // 2-bit codes of text[p, p + 16 * HL_WORDS): code = (byte >> 1) & 3, zero past the end
+        for (int w = lane; w < HL_WORDS; w += 32) {
+            const int64_t q0 = p + (int64_t)w * 16;
+            uint32_t code = 0;
+            if (q0 + 16 <= n) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + q0));     // text and p are 16-byte aligned
+                const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) code |= (((q[k] >> (8 * b)) >> 1) & 3u) << (2 * (4 * k + b));
+            } else {
+                for (int j = 0; j < 16 && q0 + j < n; j++) code |= (((uint32_t)__ldg(text + q0 + j) >> 1) & 3u) << (2 * j);
+            }
+            codes[w] = code;
+        }
+        __syncwarp();
+        const uint32_t base = codes[0];
+        for (int64_t u0 = u_lo; u0 <= u_hi; u0 += 32) {
+            const int64_t u = u0 + lane;
+            bool ok = false;
+            if (u <= u_hi && p + GK <= n - u) {
+                const uint32_t w = (uint32_t)(u >> 4), sh = (uint32_t)(u & 15) * 2u;
+                ok = __funnelshift_r(codes[w], codes[w + 1], sh) == base;
+            }
+            if (!__any_sync(0xffffffffu, ok)) continue;
+            if (ok) {
+                // on the bytes: the group really matches, and the aligned group before it does not (else that one reports)
+                const uint8_t *a = text + p;
+                for (int q = 0; q < GK && ok; q++) ok = __ldg(a + q) == __ldg(a + q + u);
+                if (ok && p >= GK) {
+                    bool prev = true;
+                    for (int q = 1; q <= GK && prev; q++) prev = __ldg(a - q) == __ldg(a - q + u);
+                    if (prev) {
+                        // the previous group matches too; it is listed (its 16-mer repeats as well) and reports the run
+                        ok = false;
+                    }
+                }
+                if (ok) {
+                    const int64_t lim = n - u;
+                    int64_t ra = p;
+                    while (ra > 0 && __ldg(text + ra - 1) == __ldg(text + ra - 1 + u)) ra--;
+                    int64_t rb = p + GK;
+                    while (rb < lim && __ldg(text + rb) == __ldg(text + rb + u)) rb++;
+                    if (rb - ra >= (mc - 1) * u) push_cand(out, u, ra, rb);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Units with (mc-1)*u < 8: one thread per position, run starts found directly.
 __global__ void __launch_bounds__(256)
     find_runs_small_kernel(const uint8_t *__restrict__ text, int64_t n, int64_t u_lo, int64_t u_hi,
@@ -536,7 +631,8 @@ static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t 
                         unsigned long long *key0, unsigned long long *key1, uint32_t *val0, uint32_t *val1,
                         unsigned long long *d_count, int64_t ccap, const rsort::Workspace &rws, cudaStream_t st,
                         const unsigned long long **sk, const uint32_t **sv, int64_t *m,
-                        const scan::Workspace *sws = nullptr, int64_t min_run_u1 = 0)
+                        const scan::Workspace *sws = nullptr, int64_t min_run_u1 = 0, const uint32_t *hint = nullptr,
+                        uint32_t *hint_list = nullptr, unsigned hint_cap = 0)
 {
     *m = 0;
     BWTK_CUDA(bwtk::zero_async(d_count, 16, st));
@@ -594,9 +690,20 @@ static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t 
         BWTK_CUDA(attr16_rc);
         BWTK_REQUIRE(smem <= (size_t)MAX_DYN_SMEM, "unit length too large for the run finder's shared-memory tile");
         dim3 grid((unsigned)tiles, (unsigned)ysplit);
-        prof::Scope ps("find_runs16_kernel", n, st);
-        find_runs16_kernel<<<grid, THREADS, smem, st>>>(d_text, n, pk_lo, u_hi, u_per_block, mc, out);
-        BWTK_LAUNCH_CHECK();
+        if (hint != nullptr && hint_list != nullptr && u_hi + 2 * GK <= (int64_t)HL_WORDS * 16 && (((uintptr_t)d_text) & 15) == 0) {
+            // only the aligned groups whose 16-mer occurs twice (the caller's hint bitmap) are compared at all
+            unsigned *d_hcount = reinterpret_cast<unsigned *>(d_count + 1);     // d_count[1] is free (zeroed above)
+            hint_list_kernel<<<(unsigned)ceil_div(ceil_div(n, GK), 256), 256, 0, st>>>(hint, n, hint_list, d_hcount, hint_cap);
+            BWTK_LAUNCH_CHECK();
+            prof::Scope ps("find_runs16_list_kernel", n, st);
+            find_runs16_list_kernel<<<NUM_SMS * 8, HL_WARPS * 32, 0, st>>>(d_text, n, hint_list, d_hcount, hint_cap, pk_lo, u_hi, mc,
+                                                                        out);
+            BWTK_LAUNCH_CHECK();
+        } else {
+            prof::Scope ps("find_runs16_kernel", n, st);
+            find_runs16_kernel<<<grid, THREADS, smem, st>>>(d_text, n, pk_lo, u_hi, u_per_block, mc, out);
+            BWTK_LAUNCH_CHECK();
+        }
     }
     unsigned long long h_cand = 0;
     { int rc = read_back(&h_cand, d_count, 8, st); if (rc) return rc; }
@@ -634,6 +741,31 @@ static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t 
         if ((int64_t)h_cand > ccap) return BWTK_EWORKSPACE;
     }
     return BWTK_OK;
+}
+
+// bit i: suffix i shares >= min_len symbols with a neighbour in suffix order
+__global__ void __launch_bounds__(256)
+    repeat_hint_kernel(const int32_t *__restrict__ sa, const int32_t *__restrict__ lcp, int64_t n, int min_len,
+                       uint32_t *__restrict__ bits)
+{
+    const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= n) return;
+    int v[4] = {0, 0, 0, 0};
+    if (j0 + 4 <= n && (((uintptr_t)lcp) & 15) == 0) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(lcp + j0));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+        for (int k = 0; k < 4 && j0 + k < n; k++) v[k] = lcp[j0 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t j = j0 + k;
+        if (j >= 1 && j < n && v[k] >= min_len) {
+            const uint32_t a = (uint32_t)__ldg(sa + j), b = (uint32_t)__ldg(sa + j - 1);
+            atomicOr(bits + (a >> 5), 1u << (a & 31));
+            atomicOr(bits + (b >> 5), 1u << (b & 31));
+        }
+    }
 }
 
 }  // namespace strict
@@ -1367,15 +1499,39 @@ extern "C" int64_t bwtk_strict_workspace_bytes(int64_t n, int64_t)
     int64_t cap = strict::cand_capacity(n);
     int64_t exact = 2 * align_up(cap * 8, 256) + 2 * align_up(cap * 4, 256) + align_up(cap, 256) +
                     align_up(cap * BWTK_REC_W * 4, 256) + rsort::workspace_bytes(cap) + scan::workspace_bytes(cap) +
-                    8192;
+                    align_up((n / strict::GK + 64) * 4, 256) + 8192;
     int64_t general = tier1::pass_ws_bytes(n) + 8192;  // max_mismatch > 0: greedy replay per unit length
     return exact > general ? exact : general;
+}
+
+extern "C" int64_t bwtk_repeat_hint_bytes(int64_t n) { return (n / 32 + 2) * 4; }
+
+extern "C" int32_t bwtk_repeat_hint(const int32_t *d_sa, const int32_t *d_lcp, int64_t n, int32_t min_len,
+                                    uint32_t *d_bits, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return BWTK_OK;
+    BWTK_REQUIRE(d_sa && d_lcp && d_bits, "null pointer");
+    BWTK_REQUIRE(min_len >= 1, "min_len must be >= 1");
+    BWTK_CUDA(bwtk::zero_async(d_bits, (size_t)bwtk_repeat_hint_bytes(n), st));
+    strict::repeat_hint_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, st>>>(d_sa, d_lcp, n, min_len, d_bits);
+    BWTK_LAUNCH_CHECK();
+    return BWTK_OK;
 }
 
 extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int64_t min_unit_len,
                                     int64_t max_unit_len, int64_t max_mismatch, int64_t min_copies,
                                     int32_t *d_rec, int64_t cap, int64_t *h_count, void *d_ws,
                                     int64_t ws_bytes, void *stream)
+{
+    return bwtk_strict_scan_hinted(d_text, n_total, min_unit_len, max_unit_len, max_mismatch, min_copies, d_rec, cap, h_count,
+                                   nullptr, 0, d_ws, ws_bytes, stream);
+}
+
+extern "C" int32_t bwtk_strict_scan_hinted(const uint8_t *d_text, int64_t n_total, int64_t min_unit_len,
+                                           int64_t max_unit_len, int64_t max_mismatch, int64_t min_copies,
+                                           int32_t *d_rec, int64_t cap, int64_t *h_count, const uint32_t *d_hint_bits,
+                                           int32_t hint_len, void *d_ws, int64_t ws_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     BWTK_REQUIRE(h_count, "null count");
@@ -1443,14 +1599,18 @@ extern "C" int32_t bwtk_strict_scan(const uint8_t *d_text, int64_t n_total, int6
     rsort::Workspace rws = rsort::carve(c, ccap);
     scan::Workspace sws = scan::carve(c, ccap);
     unsigned long long *d_count = c.take<unsigned long long>(2);
+    const int64_t hint_cap = n_total / strict::GK + 64;
+    uint32_t *hint_list = c.take<uint32_t>(hint_cap);
     if (!c.ok()) { set_error("strict workspace carve overflow"); return BWTK_EWORKSPACE; }
+    // a hint of h symbols filters groups of 16 matching positions iff h <= 16 (a repeated 16-mer repeats its prefixes)
+    const uint32_t *hint = (d_hint_bits != nullptr && hint_len >= 1 && hint_len <= strict::GK) ? d_hint_bits : nullptr;
     BWTK_CUDA(bwtk::zero_async(rws.err, sizeof(int), st));
     BWTK_CUDA(bwtk::zero_async(sws.err, sizeof(int), st));
     const unsigned long long *sk = nullptr;
     const uint32_t *sv = nullptr;
     int64_t m = 0;
     int rc = strict::collect_runs(d_text, n, min_unit_len, umax, min_copies, key0, key1, val0, val1, d_count, ccap, rws,
-                                  st, &sk, &sv, &m, &sws);
+                                  st, &sk, &sv, &m, &sws, 0, hint, hint_list, (unsigned)hint_cap);
     if (rc == BWTK_EWORKSPACE) {
         set_error("strict scan: %lld candidate runs exceed the workspace capacity %lld", (long long)m, (long long)ccap);
         return rc;

@@ -64,6 +64,7 @@ class _Lane:
         self.occ_rows = 8
         self.occ = torch.zeros(self.occ_rows * (max_n // occ_rate + 2), dtype=torch.int32, device=dev)
         self.seen = torch.zeros(max_n, dtype=torch.uint8, device=dev)
+        self.hint = torch.zeros(int(L.bwtk_repeat_hint_bytes(max_n)) // 4 + 4, dtype=torch.int32, device=dev)
         # the index build and the detectors run one after the other on one stream: one workspace
         wsb = max(int(L.bwtk_index_workspace_bytes(max_n)), int(L.bwtk_tier1_workspace_bytes(max_n)),
                   int(L.bwtk_strict_workspace_bytes(max_n, 1000)), int(L.bwtk_plateau_workspace_bytes(max_n)))
@@ -198,8 +199,13 @@ class GenomeScanner:
             self._mark(lane, "tier1")
         if "strict" in self.kinds:
             unit_cap = max(self.max_unit_len, min(n_seq // self.min_copies, 1000))   # bwt.py:3088-3096
-            c = self._rows_call(lane, used, "strict_scan", lambda rec, cap, cnt: L.bwtk_strict_scan(
-                d_text.data_ptr(), n, 1, unit_cap, 0, self.min_copies, rec, cap, cnt, wsp, wsb, st))
+            # the index is at hand: suffixes whose 16-mer occurs twice (LCP >= 16 with a neighbour) are the only places
+            # where a unit length >= 16 can repeat
+            _lib.check(L.bwtk_repeat_hint(lane.sa.data_ptr(), lane.lcp.data_ptr(), n, 16, lane.hint.data_ptr(), st),
+                       "repeat_hint")
+            c = self._rows_call(lane, used, "strict_scan", lambda rec, cap, cnt: L.bwtk_strict_scan_hinted(
+                d_text.data_ptr(), n, 1, unit_cap, 0, self.min_copies, rec, cap, cnt, lane.hint.data_ptr(), 16,
+                wsp, wsb, st))
             local["strict"] = (used, c)
             used += c
             self._mark(lane, "strict")

@@ -254,3 +254,46 @@ def test_tier1_homopolymer_floor_only_with_positive_entropy(oracle):
     for ent in (0.0, 0.5, 1.0):
         got = detect.tier1_rows(text, 9, 3, 6, ent)
         assert np.array_equal(got, oracle.tier1_scan(text, 9, 3, 6, ent)), f"min_entropy={ent}"
+
+
+def test_strict_scan_with_the_index_hint_gives_the_same_rows(oracle):
+    """bwtk_strict_scan_hinted: unit lengths >= 16 only look at aligned groups whose 16-mer occurs twice (bitmap from
+    SA + LCP).  Same rows as the plain scan and the oracle: planted contig, long repeats (every group active), an N
+    block (bytes that alias in the 2-bit codes), period-2 text, a hint of fewer symbols, and a hint that is too long
+    to be a filter (ignored)."""
+    import torch
+
+    from bwt_algorithm_b200 import detect
+    from bwt_algorithm_b200.device_index import DeviceIndex
+
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    s1 = gen_contig(150_000, 42)
+    s2 = gen_contig(60_000, 8)
+    s2[10_000:14_000] = ord("N")
+    s2[30_000:36_000] = np.tile(acgt[rng.integers(0, 4, 300)], 20)          # unit 300 x 20
+    s2[40_000:41_000] = np.tile(acgt[rng.integers(0, 4, 17)], 59)[:1000]      # unit 17
+    s3 = np.tile(np.frombuffer(b"AC", np.uint8), 6000)
+    s4 = acgt[rng.integers(0, 4, 40_000)].copy()
+    s4[5_000:5_000 + 3 * 997] = np.tile(acgt[rng.integers(0, 4, 997)], 3)     # unit 997, three copies
+    for name, s in (("planted_150k", s1), ("N_and_long_units", s2), ("period2", s3), ("unit_997", s4)):
+        text = s.tobytes() + b"$"
+        ix = DeviceIndex(text, build_lcp=True)
+        n = len(text)
+        want = oracle.strict_scan(text, 1, 1000, 0, 3)
+        plain = detect.strict_rows(ix.text, 1, 1000, 0, 3)
+        assert np.array_equal(plain, want), name
+        for hl in (16, 12, 20):
+            hint = detect.repeat_hint(ix.sa, ix.lcp, n, hl)
+            got = detect.strict_rows(ix.text, 1, 1000, 0, 3, hint=hint, hint_len=hl)
+            assert np.array_equal(got, want), f"{name}: hinted rows differ (hint_len={hl})"
+        # the bitmap itself: bit i <=> the 16-mer at i occurs again
+        hint = detect.repeat_hint(ix.sa, ix.lcp, n, 16).cpu().numpy().view(np.uint32)
+        bits = ((hint[np.arange(n) >> 5] >> (np.arange(n) & 31)) & 1).astype(bool)
+        lcp, sa = ix.lcp.cpu().numpy(), ix.sa.cpu().numpy()
+        ref = np.zeros(n, bool)
+        j = np.flatnonzero(lcp[1:] >= 16) + 1
+        ref[sa[j]] = True
+        ref[sa[j - 1]] = True
+        assert np.array_equal(bits, ref), name
+    del torch
