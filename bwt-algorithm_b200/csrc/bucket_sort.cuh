@@ -26,6 +26,8 @@
 // instead -- 64-bit keys (key, ~position) of the oversize buckets only; fused, all of its suffixes enter the
 // active list (ovf_regroup_kernel).  If most of the text is in such buckets the caller keeps the plain LSD path.
 #pragma once
+#include <stdlib.h>
+
 #include "radix_sort.cuh"
 #include "scan.cuh"
 
@@ -438,9 +440,9 @@ struct SumComb64 {
 // before longer suffixes with the same zero-padded key, shortest first)
 template <bool FUSED>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
-    bucket_sort_kernel(const uint2 *__restrict__ pairs, int64_t n, int nb_bits, int64_t short_from,
-                       const uint32_t *__restrict__ bstart, uint32_t *__restrict__ skey, uint32_t *__restrict__ sval,
-                       unsigned *ticket, Regroup rg)
+    bucket_sort_kernel(const uint2 *__restrict__ pairs, const uint32_t *__restrict__ packed, int64_t n, int nb_bits,
+                       int64_t short_from, const uint32_t *__restrict__ bstart, uint32_t *__restrict__ skey,
+                       uint32_t *__restrict__ sval, unsigned *ticket, Regroup rg, int refine)
 {
     extern __shared__ __align__(16) uint32_t sm[];
     uint32_t *s_pos = sm;                                      // [CAP_EFF + 16] position of the element in slot i
@@ -638,10 +640,11 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
     if (!FUSED) return;
 
     // ---- fused regroup: heads, active list, ranks, prefix table -----------------------------------
-    // s_b is free again: [0, 256) head bits, [256, 512) active bits, [512, 768) last head at or before the
-    // start of each 32-element word, [768, 1024) active elements before each word.
+    // s_h is free again: [0, 256) head bits of the 16-symbol groups, [256, 512) active bits, [512, 768) last head at
+    // or before the start of each 32-element word, [768, 1024) active elements before each word, [1024, 1280) head
+    // bits after the in-bucket refinement (what everything below uses); s_b holds the second keys.
     __syncthreads();
-    uint32_t *s_hb = s_b, *s_ab = s_b + 256, *s_wh = s_b + 512, *s_wa = s_b + 768;
+    uint32_t *s_hb0 = s_h, *s_ab = s_h + 256, *s_wh = s_h + 512, *s_wa = s_h + 768, *s_hb = s_h + 1024;
     uint32_t n_active = 0;
     if (sorted_here) {
         const int words = (int)((cnt + 31) >> 5);
@@ -666,9 +669,73 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
                 }
             }
             const unsigned hb = __ballot_sync(0xffffffffu, head);
-            if (lane == 0) s_hb[j0 >> 5] = hb;
+            if (lane == 0) { s_hb0[j0 >> 5] = hb; s_hb[j0 >> 5] = hb; }
         }
         __syncthreads();
+        if (refine) {
+            // Round 1 of the doubling (h = 16) for the small groups, here: a group of 2..32 suffixes with equal keys
+            // that lies inside one 32-element window of the sorted bucket is ordered by the NEXT 16 symbols (the
+            // round-0 key of suffix + 16, which is what rank[suffix + 16] orders by) and split where they differ.
+            // Members that become singletons are final and never enter the active list; groups that straddle a
+            // window, larger groups and groups that touch the end of the text stay 16-symbol groups.  The global
+            // rounds that follow are unchanged -- a group that is already finer than the round's h is only sorted
+            // again by ranks that are finer still.  Everything is warp-local: one bitmap word = one window.
+            for (uint32_t j0 = warp * 32; j0 < cnt; j0 += SORT_THREADS) {
+                const uint32_t w = j0 >> 5;
+                const uint32_t hbw = s_hb0[w];                                   // padding lanes of the last window are heads
+                const bool next_head = (w + 1 >= (uint32_t)words) || (s_hb0[w + 1] & 1u);
+                if (hbw == 0xffffffffu && next_head) {                           // singletons only
+                    if (lane == 0) s_hb[w] = hbw;
+                    continue;
+                }
+                const uint32_t below = hbw & (0xffffffffu >> (31 - lane));       // heads at or before this lane
+                const uint32_t above = lane < 31 ? (hbw >> (lane + 1)) : 0u;      // heads after it
+                const bool inside = below != 0u && (above != 0u || next_head);  // the whole group lies in this window
+                const uint32_t lo = below ? 31u - (uint32_t)__clz(below) : 0u;
+                const uint32_t hi = above ? lane + 1u + (uint32_t)(__ffs(above) - 1) : 32u;
+                const uint32_t size = hi - lo;
+                const uint32_t j = j0 + lane;
+                const uint32_t x = j < cnt ? s_a[j] : 0u;
+                // second key of the members of whole groups of >= 2: the round-0 key of suffix + 16 (all ones also
+                // stands for "touches the end of the text")
+                uint32_t k2 = 0u;
+                if (j < cnt && inside && size >= 2u) {
+                    const int64_t q = (int64_t)s_pos[x & (CAP - 1)] + 16;
+                    k2 = q < short_from ? window32(packed, q * 2) : 0xffffffffu;
+                }
+                // a group is refined when it is whole, has >= 2 members, and none of them touches the end of the text
+                // (a true second key of all ones cannot tie with a smaller one, so treating it as "touches" only
+                // leaves that group to the global round)
+                const unsigned touch = __ballot_sync(0xffffffffu, j < cnt && k2 == 0xffffffffu);
+                const uint32_t gmask = size >= 32u ? 0xffffffffu : (((1u << size) - 1u) << lo);
+                const bool refine_me = j < cnt && inside && size >= 2u && (touch & gmask) == 0u;
+                const unsigned any = __ballot_sync(0xffffffffu, refine_me);
+                uint32_t newpos = lane;
+                bool head2 = (hbw >> lane) & 1u;
+                if (any) {
+                    const uint32_t maxsize = __reduce_max_sync(0xffffffffu, refine_me ? size : 0u);
+                    uint32_t r = 0, eqbefore = 0;
+                    for (uint32_t d = 0; d < maxsize; d++) {
+                        const uint32_t xl = (lo + d) & 31u;
+                        const uint32_t kx = __shfl_sync(0xffffffffu, k2, xl);
+                        const bool valid = refine_me && d < size;
+                        r += (valid && (kx < k2 || (kx == k2 && xl < (uint32_t)lane))) ? 1u : 0u;
+                        eqbefore += (valid && kx == k2 && xl < (uint32_t)lane) ? 1u : 0u;
+                    }
+                    if (refine_me) {
+                        newpos = lo + r;
+                        head2 = eqbefore == 0u;          // first of its (key, second key) class
+                    }
+                }
+                const uint32_t hb2 = __reduce_or_sync(0xffffffffu, head2 ? (1u << newpos) : 0u);
+                if (any) {
+                    __syncwarp();
+                    if (refine_me) s_a[j0 + newpos] = x;     // a permutation inside the group: every lane has read its x
+                }
+                if (lane == 0) s_hb[w] = hb2;
+            }
+            __syncthreads();
+        }
         // per-word carries: 256 words at most, 8 per lane of warp 0 (max-scan of heads, sum-scan of actives);
         // an element is active unless it and its successor are both heads
         if (warp == 0) {
@@ -858,6 +925,13 @@ __global__ void ovf_regroup_kernel(const unsigned long long *__restrict__ sk, co
     }
 }
 
+// BWTK_MSD_REFINE=0 switches the in-bucket refinement of small groups off (tuning and tests)
+static bool refine_enabled()
+{
+    const char *e = getenv("BWTK_MSD_REFINE");
+    return !(e && atoi(e) == 0);
+}
+
 // Sorts the n suffixes of a 2-bit packed text by their 32-bit round-0 key (ties: suffixes that run off the
 // text first, shortest first; the rest in no particular order).
 //   fused == nullptr : sorted keys -> skey, suffixes -> sval (what the LSD sort delivers);
@@ -936,15 +1010,16 @@ static int round0_sort(const uint32_t *packed, int64_t n, const Workspace &ws, c
         rg.ovf_abase = ws.fill;    // the claim cursors are dead once fine_scatter has run
         rgf = rg;
         prof::Scope ps("bucket_sort_regroup", n * 16, st);
-        bucket_sort_kernel<true><<<(unsigned)nbk, SORT_THREADS, sort_smem(), st>>>(pairs_b, n, nb, short_from, ws.bstart,
-                                                                                   skey, sval, ws.ticket, rg);
+        bucket_sort_kernel<true><<<(unsigned)nbk, SORT_THREADS, sort_smem(), st>>>(pairs_b, packed, n, nb, short_from,
+                                                                                   ws.bstart, skey, sval, ws.ticket, rg,
+                                                                                   refine_enabled() ? 1 : 0);
         BWTK_LAUNCH_CHECK();
         *did_fuse = true;
     } else {
         Regroup rg{};
         prof::Scope ps("bucket_sort", n * 16, st);
-        bucket_sort_kernel<false><<<(unsigned)nbk, SORT_THREADS, sort_smem(), st>>>(pairs_b, n, nb, short_from, ws.bstart,
-                                                                                    skey, sval, ws.ticket, rg);
+        bucket_sort_kernel<false><<<(unsigned)nbk, SORT_THREADS, sort_smem(), st>>>(pairs_b, packed, n, nb, short_from,
+                                                                                    ws.bstart, skey, sval, ws.ticket, rg, 0);
         BWTK_LAUNCH_CHECK();
     }
     if (info.ovf_buckets) {
