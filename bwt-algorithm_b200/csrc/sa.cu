@@ -502,7 +502,7 @@ static bool msd_enabled(int64_t n)
     const char *e = getenv("BWTK_MSD");
     if (e && atoi(e) == 0) return false;
     const char *m = getenv("BWTK_MSD_MIN_N");
-    const int64_t min_n = m ? atoll(m) : (1ll << 21);
+    const int64_t min_n = m ? atoll(m) : (1ll << 24);
     return n >= min_n;
 }
 static bool msd_fuse_enabled()

@@ -97,7 +97,7 @@ int32_t bwtk_byte_histogram(const uint8_t *d_text, int64_t n, int64_t *h_totals,
  * h_stats (may be NULL) receives int64[8]: rounds, bits/symbol, symbols/key,
  * active after round 0, sum of active over rounds, radix passes, path flags, 0.
  * Path flags: bit 0 = ACGT$ 2-bit layout, bit 1 = round 0 by the MSD bucket sort
- * (2-bit texts from 2^21 symbols on; environment BWTK_MSD=0 keeps the LSD sort,
+ * (2-bit texts from 2^24 symbols on -- below that the four LSD passes are faster; environment BWTK_MSD=0 keeps the LSD sort,
  * BWTK_MSD_MIN_N=<n> moves the threshold), bit 2 = first regroup pass fused into it
  * (BWTK_MSD_FUSE=0 switches the fusion off).  The suffix array does not depend on the path.
  * Synchronises the stream (one 4-byte read-back per doubling round). */

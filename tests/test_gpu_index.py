@@ -508,7 +508,7 @@ def _bucket_sort_texts():
 @pytest.mark.parametrize("fuse", ["1", "0", "norefine"], ids=["fused", "unfused", "fused_without_refinement"])
 @pytest.mark.parametrize("name,text", _bucket_sort_texts(), ids=[c[0] for c in _bucket_sort_texts()])
 def test_round0_bucket_sort_matches_oracle(DeviceIndex, oracle, monkeypatch, name, text, fuse):
-    """The MSD bucket sort is only taken from 2 M symbols on; here it is forced on small texts (normal
+    """The MSD bucket sort is only taken from 16 M symbols on; here it is forced on small texts (normal
     buckets, oversize buckets through the LSD sort, large sub-buckets through the bitonic path, short
     suffixes) and must give the same SA / ISA / BWT / Occ / LCP as the oracle, fused and unfused."""
     monkeypatch.setenv("BWTK_MSD_MIN_N", "0")
