@@ -294,6 +294,30 @@ __global__ void __launch_bounds__(256)
     for (int64_t blk = warp_g; blk < nblk; blk += nwarps) {
         int64_t j0 = blk * occ_rate;
         int64_t j1 = j0 + occ_rate < n ? j0 + occ_rate : n;
+        if (PACKED) {
+            // five symbols: counts by ballot (every lane ends up with the block's totals), one store per row
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+            for (int64_t jb = j0; jb < j1; jb += 32) {
+                const int64_t j = jb + lane;
+                uint32_t code = 5u;                                   // past the end of the block
+                if (j < j1) {
+                    const int64_t p = (int64_t)__ldg(sa + j) - 1;
+                    code = p >= 0 ? (__ldg(packed + (p >> 4)) >> (30 - 2 * (int)(p & 15))) & 3u : 4u;
+                    bwt[j] = (uint8_t)((0x2454474341ull >> (8 * code)) & 0xffu);   // "ACGT$"
+                }
+                c0 += __popc(__ballot_sync(0xffffffffu, code == 0u));
+                c1 += __popc(__ballot_sync(0xffffffffu, code == 1u));
+                c2 += __popc(__ballot_sync(0xffffffffu, code == 2u));
+                c3 += __popc(__ballot_sync(0xffffffffu, code == 3u));
+                c4 += __popc(__ballot_sync(0xffffffffu, code == 4u));
+            }
+            if (lane < 5) {
+                const int v = lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : lane == 3 ? c3 : c4;
+                const int r = s_row[(int)((0x2454474341ull >> (8 * lane)) & 0xffu)];
+                if (r >= 0) occ[(int64_t)r * ncp + blk + 1] = v;
+            }
+            continue;
+        }
         for (int rg = 0; rg < nrows; rg += 8) {
             int cnt[8];
 #pragma unroll
@@ -302,13 +326,8 @@ __global__ void __launch_bounds__(256)
                 uint8_t c;
                 if (rg == 0) {
                     int64_t p = (int64_t)__ldg(sa + j) - 1;
-                    if (PACKED) {
-                        const uint32_t code = p >= 0 ? (__ldg(packed + (p >> 4)) >> (30 - 2 * (int)(p & 15))) & 3u : 4u;
-                        c = (uint8_t)((0x2454474341ull >> (8 * code)) & 0xffu);   // "ACGT$"
-                    } else {
-                        if (p < 0) p += n;
-                        c = __ldg(text + p);
-                    }
+                    if (p < 0) p += n;
+                    c = __ldg(text + p);
                     bwt[j] = c;
                 } else {
                     c = bwt[j];
