@@ -433,7 +433,8 @@ template <int U> struct SmallRuns {
     const uint8_t *text;    // 16-byte aligned
     int64_t n;
     int64_t L;              // minimum run length
-    // bit j: text[p0 + j] == text[p0 + j + U] (and p0 + j < n - U), j = 0..15; *prev: the same for p0 - 1
+    // bit j: text[p0 + j] == text[p0 + j + U] (and p0 + j < n - U), j = 0..23 -- the chunk's 16 positions and 8 of
+    // look-ahead, enough to see whether a run of <= 9 starts at any of them; *prev: the same for p0 - 1
     __device__ __forceinline__ uint32_t mask(int64_t p0, bool *prev) const
     {
         const int64_t lim = n - U;
@@ -442,20 +443,23 @@ template <int U> struct SmallRuns {
             const uint4 a = __ldg(reinterpret_cast<const uint4 *>(text + p0));
             const uint4 b = __ldg(reinterpret_cast<const uint4 *>(text + p0 + 16));
             const unsigned long long w0 = ((unsigned long long)a.y << 32) | a.x, w1 = ((unsigned long long)a.w << 32) | a.z,
-                                     w2 = ((unsigned long long)b.y << 32) | b.x;
-            // bytes j + U of the two 8-byte halves
-            const unsigned long long s0 = (w0 >> (8 * U)) | (w1 << (64 - 8 * U)), s1 = (w1 >> (8 * U)) | (w2 << (64 - 8 * U));
-            unsigned long long x0 = w0 ^ s0, x1 = w1 ^ s1;
+                                     w2 = ((unsigned long long)b.y << 32) | b.x, w3 = ((unsigned long long)b.w << 32) | b.z;
+            // bytes j + U of the three 8-byte words
+            const unsigned long long s0 = (w0 >> (8 * U)) | (w1 << (64 - 8 * U)), s1 = (w1 >> (8 * U)) | (w2 << (64 - 8 * U)),
+                                     s2 = (w2 >> (8 * U)) | (w3 << (64 - 8 * U));
+            unsigned long long x0 = w0 ^ s0, x1 = w1 ^ s1, x2 = w2 ^ s2;
             // zero bytes -> bit 7 of the byte (exact form: no borrow across bytes)
             const unsigned long long K = 0x7f7f7f7f7f7f7f7full;
             x0 = ~(((x0 & K) + K) | x0 | K);
             x1 = ~(((x1 & K) + K) | x1 | K);
+            x2 = ~(((x2 & K) + K) | x2 | K);
             // bit 7 of every byte -> one byte (the multiply adds the eight bits up in its top byte)
             e = (uint32_t)(((x0 >> 7) * 0x0102040810204080ull) >> 56) |
-                ((uint32_t)(((x1 >> 7) * 0x0102040810204080ull) >> 56) << 8);
-            if (p0 + 16 > lim) e &= lim > p0 ? ((1u << (int)(lim - p0)) - 1u) : 0u;
+                ((uint32_t)(((x1 >> 7) * 0x0102040810204080ull) >> 56) << 8) |
+                ((uint32_t)(((x2 >> 7) * 0x0102040810204080ull) >> 56) << 16);
+            if (p0 + 24 > lim) e &= lim > p0 ? ((1u << (int)(lim - p0)) - 1u) : 0u;
         } else {
-            for (int j = 0; j < 16; j++) {
+            for (int j = 0; j < 24; j++) {
                 const int64_t q = p0 + j;
                 if (q < lim && __ldg(text + q) == __ldg(text + q + U)) e |= 1u << j;
             }
@@ -463,23 +467,30 @@ template <int U> struct SmallRuns {
         *prev = p0 > 0 && p0 - 1 < lim && __ldg(text + p0 - 1) == __ldg(text + p0 - 1 + U);
         return e;
     }
+    // bit j (j < 16): a maximal run of >= L matches starts at p0 + j.  L <= 9: the 24-bit mask decides.
+    __device__ __forceinline__ uint32_t qualifying_starts(uint32_t e, bool prev) const
+    {
+        uint32_t r = e;
+        for (int k = 1; k < (int)L; k++) r &= e >> k;
+        return e & ~((e << 1) | (prev ? 1u : 0u)) & r & 0xffffu;
+    }
     // calls f(start, end) for every maximal run of >= L matches that starts in the chunk with match mask e
     template <typename F> __device__ __forceinline__ void for_runs(int64_t c, uint32_t e, bool prev, F f) const
     {
         const int64_t p0 = c * 16;
-        uint32_t starts = e & ~((e << 1) | (prev ? 1u : 0u)) & 0xffffu;
+        uint32_t starts = qualifying_starts(e, prev);
         const int64_t lim = n - U;
         while (starts) {
             const int j = __ffs(starts) - 1;
             starts &= starts - 1;
             const uint32_t rest = ~(e >> j);                 // first mismatch after j
-            int t = __ffs(rest) - 1;                          // e has 16 bits: a zero always exists at or below bit 16 - j
+            const int t = __ffs(rest) - 1;                    // e has 24 bits: a zero exists at or below bit 24 - j
             int64_t b = p0 + j + t;
-            if (j + t >= 16) {                                // the run leaves the chunk
-                b = p0 + 16;
+            if (j + t >= 24) {                                // the run leaves what the mask covers
+                b = p0 + 24;
                 while (b < lim && __ldg(text + b) == __ldg(text + b + U)) b++;
             }
-            if (b - (p0 + j) >= L) f(p0 + j, b);
+            f(p0 + j, b);
         }
     }
 };
@@ -500,9 +511,7 @@ template <int U> struct SmallRunsCount {
         const uint32_t e = sr.mask(c * 16, &prev);
         ctx.e[k] = e;
         if (prev) ctx.prev |= 1u << k;
-        unsigned cnt = 0;
-        sr.for_runs(c, e, prev, [&](int64_t, int64_t) { cnt++; });
-        return cnt;
+        return (unsigned long long)__popc(sr.qualifying_starts(e, prev));
     }
 };
 template <int U> struct SmallRunsEmit {
@@ -643,7 +652,8 @@ static int collect_runs(const uint8_t *d_text, int64_t n, int64_t u_lo, int64_t 
     int64_t small_hi = 7 / (mc - 1);
     if (small_hi > u_hi) small_hi = u_hi;
     // ordered form (no atomics, no sort) when a scan workspace is given and the text allows 16-byte loads
-    const bool ordered = sws != nullptr && small_hi >= u_lo && small_hi <= 7 && (((uintptr_t)d_text) & 15) == 0;
+    const bool ordered = sws != nullptr && small_hi >= u_lo && small_hi <= 7 && (((uintptr_t)d_text) & 15) == 0 &&
+                         (mc - 1) * small_hi <= 9 && (min_run_u1 <= 9);   // the 24-bit match mask decides runs of <= 9
     if (small_hi >= u_lo && !ordered) {
         find_runs_small_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_text, n, u_lo, small_hi, mc, min_run_u1, out);
         BWTK_LAUNCH_CHECK();
