@@ -50,6 +50,8 @@ _SIGS = {
     "bwtk_fasta_index": (_i32, [_p, _i64, _p, _i64, _p, _p]),
     "bwtk_fasta_sequence": (_i64, [_p, _i64, _i64, _i64, _i64, _i32, _p]),
     "bwtk_suppress_nested": (_i32, [_p, _p, _p, _p, _i64, C.c_double, _p]),
+    "bwtk_align_repeat_region": (_i32, [C.c_char_p, _i64, _i64, _i64, C.c_char_p, _i32, _i32, _i32, _i32, _p, _p, _p,
+                                        _i64]),
     "bwtk_byte_histogram": (_i32, [_p, _i64, _p, _p]),
     "bwtk_sa_workspace_bytes": (_i64, [_i64]),
     "bwtk_sa_build": (_i32, [_p, _i64, _p, _p, _p, _i64, _p, _p]),

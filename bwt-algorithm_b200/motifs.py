@@ -481,3 +481,62 @@ class MotifUtils:
 @functools.lru_cache(maxsize=1 << 17)
 def _align_unit_cached(motif: str, window: str, max_indel: int, mismatch_tolerance: int):
     return MotifUtils._align_unit_to_window_dp(motif, window, max_indel, mismatch_tolerance)
+
+
+# ---- native copy-by-copy walk (csrc/rowchain.cu: bwtk_align_repeat_region) ---------------------------------
+_NOTES_BUF = _CONS_BUF = _OUT_BUF = None
+_NATIVE_WALK = None      # False once the library turned out to be unavailable
+
+
+def align_region_native(seq_bytes: bytes, start: int, end: int, template: bytes, mismatch_fraction: float = 0.1,
+                        max_indel: Optional[int] = None, min_copies: int = 3):
+    """``MotifUtils.align_repeat_region`` on the ASCII bytes of a contig, in native code.
+
+    Returns the fields ``_recompute_repeat`` reads -- (consensus str, copies, consumed_length, mismatch_rate,
+    max_errors_per_copy, variations, total_insertions, total_deletions) --, ``None`` where the reference
+    returns None, or ``NotImplemented`` when the native walk does not apply (library missing, a consensus
+    column with more than 8 distinct symbols): the caller then runs the Python walk, which defines the
+    behaviour (tests/test_host_glue_cpu.py holds the two equal on random and planted sequences)."""
+    global _NOTES_BUF, _CONS_BUF, _OUT_BUF, _NATIVE_WALK
+    import ctypes as C
+
+    if _NATIVE_WALK is False:
+        return NotImplemented
+    if _NATIVE_WALK is None:
+        from . import _lib
+
+        try:
+            _NATIVE_WALK = _lib.lib().bwtk_align_repeat_region
+        except Exception:
+            _NATIVE_WALK = False
+            return NotImplemented
+        _NOTES_BUF = C.create_string_buffer(1 << 12)
+        _CONS_BUF = C.create_string_buffer(1 << 10)
+        _OUT_BUF = (C.c_int64 * 8)()
+    k = len(template)
+    if k == 0 or not seq_bytes:
+        return None
+    tol = max(1, int(math.floor(k * mismatch_fraction)))
+    if max_indel is None:
+        max_indel = max(1, min(10, k // 2 if k >= 4 else 1))
+    else:
+        max_indel = max(0, max_indel)
+    if k > len(_CONS_BUF):
+        _CONS_BUF = C.create_string_buffer(2 * k)
+    cons, out = _CONS_BUF, _OUT_BUF
+    while True:
+        rc = _NATIVE_WALK(seq_bytes, len(seq_bytes), start, end, template, k, tol, max_indel, min_copies,
+                          cons, out, _NOTES_BUF, len(_NOTES_BUF))
+        if rc == -4:                                     # BWTK_EOVERFLOW: the notes need a larger buffer
+            _NOTES_BUF = C.create_string_buffer(int(out[7]) * 2)
+            continue
+        break
+    if rc == 0:
+        return None
+    if rc != 1:
+        return NotImplemented
+    copies, consumed, errs, worst, n_ins, n_del, n_notes, note_bytes = out
+    denom = copies * k
+    notes = _NOTES_BUF.raw[:note_bytes].decode("ascii").split("\n") if n_notes else []
+    return (cons.raw[:k].decode("ascii"), copies, consumed, (errs / denom if denom > 0 else 0.0), worst, notes,
+            n_ins, n_del)

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Tuple
 
 from .core import BWTCore
 from .finders import Tier2LCPFinder
-from .motifs import MotifUtils
+from .motifs import MotifUtils, align_region_native
 from .records import TandemRepeat, _natural_sort_key
 
 _BAR = 40
@@ -141,6 +141,9 @@ def _process_and_finish_contig(args):
         traceback.print_exc()
         return [], n_raw, n_raw, n_raw
 
+
+# consensus motif -> (strand, composition, entropy) for _recompute_repeat (pure functions of the string)
+_PER_CONSENSUS: Dict[str, tuple] = {}
 
 # Pinned host copies (trimmed text + '$') of the contigs of the FASTA loaded last, filled by the native
 # parser; the in-process worker uploads from here.  Worker processes (one per GPU) do not see it and
@@ -663,11 +666,9 @@ class TandemRepeatFinder:
             template = sequence[back:back + motif_len]
         if not template:
             template = "N" * motif_len
-        summary = MotifUtils.align_repeat_region(sequence, start, end, template, mismatch_fraction=0.1,
-                                                 min_copies=max(1, self.min_copies))
+        summary = self._align_walk(chrom, sequence, start, end, template, max(1, self.min_copies))
         if summary is None:
-            summary = MotifUtils.align_repeat_region(sequence, start, end, template, mismatch_fraction=0.1,
-                                                     min_copies=1)
+            summary = self._align_walk(chrom, sequence, start, end, template, 1)
         if summary is None:
             consumed = min(total - start, max(motif_len, end - start))
             actual = sequence[start:start + consumed]
@@ -675,29 +676,58 @@ class TandemRepeatFinder:
             consensus = template if template else (actual[:motif_len] or "N")
             mm_rate, worst, pct_indel, notes = 0.0, 0, 0.0, None
         else:
-            actual = sequence[start:start + summary.consumed_length]
-            n_copies = summary.copies
-            consensus = summary.consensus or template
-            mm_rate = summary.mismatch_rate
-            cells = summary.copies * summary.motif_len
-            pct_indel = ((summary.total_insertions + summary.total_deletions) / cells if cells > 0 else 0.0) * 100.0
-            worst = summary.max_errors_per_copy
-            notes = summary.variations if summary.variations else None
+            s_cons, n_copies, s_consumed, mm_rate, worst, s_notes, s_ins, s_del = summary
+            actual = sequence[start:start + s_consumed]
+            consensus = s_cons or template
+            cells = n_copies * len(template)
+            pct_indel = ((s_ins + s_del) / cells if cells > 0 else 0.0) * 100.0
+            notes = s_notes if s_notes else None
         span = len(actual)
         k_eff = len(consensus) if consensus else motif_len
         copies = float(n_copies)
         if span > 0 and k_eff > 0:
             frac = span / k_eff
             copies = float(round(frac)) if abs(frac - round(frac)) < 1e-6 else frac
-        return TandemRepeat(
-            chrom=chrom, start=start, end=start + span, motif=consensus, copies=copies, length=span, tier=tier_hint,
-            confidence=max(0.3, 1.0 - mm_rate), consensus_motif=consensus, mismatch_rate=mm_rate,
-            max_mismatches_per_copy=worst, n_copies_evaluated=max(1, n_copies),
-            strand=MotifUtils.get_canonical_motif_stranded(consensus)[1],
-            percent_matches=max(0.0, 100.0 - mm_rate * 100.0), percent_indels=pct_indel,
-            score=MotifUtils.calculate_trf_score(consensus, max(1, n_copies), mm_rate, span),
-            composition=MotifUtils.calculate_composition(consensus), entropy=MotifUtils.calculate_entropy(consensus),
-            actual_sequence=actual, variations=notes)
+        # strand, composition and entropy are functions of the consensus alone, and a contig's merges ask for the
+        # same few consensus motifs over and over
+        known = _PER_CONSENSUS.get(consensus)
+        if known is None:
+            if len(_PER_CONSENSUS) >= 1 << 16:
+                _PER_CONSENSUS.clear()
+            known = _PER_CONSENSUS[consensus] = (MotifUtils.get_canonical_motif_stranded(consensus)[1],
+                                                 MotifUtils.calculate_composition(consensus),
+                                                 MotifUtils.calculate_entropy(consensus))
+        strand, comp, ent = known
+        # positional, in the field order of records.TandemRepeat (bwt.py:429-452)
+        return TandemRepeat(chrom, start, start + span, consensus, copies, span, tier_hint, max(0.3, 1.0 - mm_rate),
+                            consensus, mm_rate, worst, max(1, n_copies), strand, max(0.0, 100.0 - mm_rate * 100.0),
+                            pct_indel, MotifUtils.calculate_trf_score(consensus, max(1, n_copies), mm_rate, span),
+                            dict(comp), ent, actual, notes)
+
+    _NATIVE_WALK = True    # tests switch it off to compare with the Python walk
+
+    def _align_walk(self, chrom: str, sequence: str, start: int, end: int, template: str, min_copies: int):
+        """``MotifUtils.align_repeat_region(sequence, start, end, template, 0.1, min_copies=...)`` reduced to
+        the fields _recompute_repeat reads: (consensus, copies, consumed_length, mismatch_rate,
+        max_errors_per_copy, variations, total_insertions, total_deletions) or None.  ASCII contigs take the
+        native walk over the contig's bytes (bwtk_align_repeat_region, the same walk answer for answer);
+        anything else, and whatever the native walk declines, goes through the Python one."""
+        if self._NATIVE_WALK:
+            memo = self.__dict__.setdefault("_seq_bytes", {})
+            got = memo.get(chrom)
+            if got is None or got[0] is not sequence:
+                got = (sequence, sequence.encode("ascii") if sequence.isascii() else None)
+                memo[chrom] = got
+            if got[1] is not None and template.isascii():
+                res = align_region_native(got[1], start, end, template.encode("ascii"), 0.1, None, min_copies)
+                if res is not NotImplemented:
+                    return res
+        summ = MotifUtils.align_repeat_region(sequence, start, end, template, mismatch_fraction=0.1,
+                                              min_copies=min_copies)
+        if summ is None:
+            return None
+        return (summ.consensus, summ.copies, summ.consumed_length, summ.mismatch_rate, summ.max_errors_per_copy,
+                summ.variations, summ.total_insertions, summ.total_deletions)
 
     # ------------------------------------------------------------------ compound repeats (strfinder writer)
     @staticmethod

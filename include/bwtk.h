@@ -85,6 +85,23 @@ int64_t bwtk_fasta_sequence(const uint8_t *buf, int64_t body_off, int64_t body_e
 int32_t bwtk_suppress_nested(const int32_t *start, const int32_t *end, const int32_t *motif_len,
                              const uint8_t *imperfect, int64_t n, double overlap_threshold, uint8_t *keep);
 
+/* ---- post-processing: MotifUtils.align_repeat_region (bwt.py:997-1102) with its per-copy aligner
+ * MotifUtils._align_unit_to_window (bwt.py:828-995), host code, on the bytes of one contig.  The walk
+ * starts at `start` with the template `motif` (k bytes), takes runs of exact copies in one step, aligns every
+ * other copy by the banded unit-cost DP (ties substitution > deletion > insertion; end column = first
+ * minimum in [k - max_indel, k + max_indel]; rejected above `tol` substitutions or `max_indel` inserted /
+ * deleted bases) and re-derives the consensus (per column the first maximum in first-seen order) after it.
+ * tol and max_indel are the values the reference derives from mismatch_fraction / its default rule.
+ * out = int64[8]: copies, consumed length, sum of per-copy errors, max errors per copy, inserted bases,
+ * deleted bases, number of variation notes, bytes of notes.  consensus: k bytes.  notes: the reference's
+ * `variations` strings ("copy:pos:X>Y", "copy:pos:ins(S)", "copy:pos:del(n)") joined by '\n'.
+ * Returns 1 (summary written), 0 (the reference returns None), BWTK_EOVERFLOW (notes_cap too small, out[7]
+ * holds the size), BWTK_EWORKSPACE (a column saw more than 8 distinct symbols: use the generic walk). */
+int32_t bwtk_align_repeat_region(const uint8_t *seq, int64_t total, int64_t start, int64_t end,
+                                 const uint8_t *motif, int32_t k, int32_t tol, int32_t max_indel,
+                                 int32_t min_copies, uint8_t *consensus, int64_t *out, uint8_t *notes,
+                                 int64_t notes_cap);
+
 /* ---- a5: BWTCore._build_char_counts (bwt.py:276-286) ------------------
  * byte histogram of the text; h_totals[256] (host) receives the counts.
  * The exclusive prefix sum over present bytes (the FM "C" array) is a 256-entry

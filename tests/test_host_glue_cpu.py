@@ -134,6 +134,112 @@ def test_exact_copy_fast_path_equals_dp_walk():
     assert checked == 800 and hits > 50   # mixed exact / inexact walks were exercised
 
 
+def _walk_fields(summary):
+    if summary is None:
+        return None
+    return (summary.consensus, summary.copies, summary.consumed_length, summary.mismatch_rate,
+            summary.max_errors_per_copy, summary.variations, summary.total_insertions, summary.total_deletions)
+
+
+def test_native_walk_equals_python_walk():
+    """bwtk_align_repeat_region (csrc/rowchain.cu) is MotifUtils.align_repeat_region answer for answer: consensus,
+    copies, consumed span, mismatch rate, worst copy, variation notes, inserted / deleted bases -- on mutated
+    tandem arrays over several alphabets, with templates, spans, indel bands and copy floors of every kind."""
+    import random
+
+    from bwt_algorithm_b200.motifs import align_region_native
+
+    rng = random.Random(41)
+
+    def mk(alpha, n):
+        return "".join(rng.choice(alpha) for _ in range(n))
+
+    cases = summaries = with_sub = with_ins = with_del = 0
+    for _ in range(1200):
+        alpha = rng.choice(["ACGT", "ACGT", "AC", "ACGTN", "ACGTNRYK"])
+        k = rng.choice([1, 1, 2, 3, 4, 5, 6, 7, 9, 12, 13, 17, 30, 64, 150])
+        motif = mk(alpha, k)
+        parts = [mk(alpha, rng.randrange(0, 40))]
+        for _ in range(rng.randrange(1, 4)):
+            arr = list(motif * rng.randrange(1, 12))
+            for _ in range(rng.randrange(0, max(1, len(arr) // 8) + 1)):
+                p, r = rng.randrange(len(arr)), rng.random()
+                if r < 0.5:
+                    arr[p] = rng.choice(alpha)
+                elif r < 0.75:
+                    arr.insert(p, rng.choice(alpha))
+                elif len(arr) > 1:
+                    del arr[p]
+            parts += ["".join(arr), mk(alpha, rng.randrange(0, 30))]
+        seq = "".join(parts)
+        seq_bytes = seq.encode("ascii")
+        for _ in range(5):
+            start = rng.randrange(-2, len(seq))
+            end = rng.choice([0, start, start + rng.randrange(1, 200), len(seq) + 5])
+            kk = rng.choice([k, k, max(1, k - 1), k + 1])
+            template = seq[max(0, start):max(0, start) + kk] if rng.random() < 0.8 else mk(alpha, kk)
+            if not template:
+                continue
+            min_copies = rng.choice([1, 2, 3, 3, 5])
+            max_indel = rng.choice([None, None, 0, 1, 3])
+            frac = rng.choice([0.1, 0.1, 0.0, 0.25])
+            want = _walk_fields(MotifUtils.align_repeat_region(seq, start, end, template, frac, max_indel, min_copies))
+            got = align_region_native(seq_bytes, start, end, template.encode("ascii"), frac, max_indel, min_copies)
+            assert got is not NotImplemented
+            assert got == want, (seq, start, end, template, frac, max_indel, min_copies)
+            cases += 1
+            if want is not None:
+                summaries += 1
+                with_sub += any(">" in v for v in want[5])
+                with_ins += any("ins(" in v for v in want[5])
+                with_del += any("del(" in v for v in want[5])
+    assert cases > 5000 and summaries > 1500 and min(with_sub, with_ins, with_del) > 40
+
+
+def test_native_walk_declines_what_it_cannot_represent():
+    """More than eight distinct symbols in one consensus column: the native walk says NotImplemented and
+    _recompute_repeat takes the Python walk -- same record either way; a non-ASCII contig never reaches it."""
+    from bwt_algorithm_b200.motifs import align_region_native
+
+    column = "ABCDEFGHIJ"
+    seq = "".join(c + "CGT" for c in column) + "ACGT" * 3
+    assert align_region_native(seq.encode(), 0, len(seq), b"ACGT", 0.25, None, 1) is NotImplemented
+    for text in (seq, "ACGÅ" * 6 + "TTTT"):
+        recs = []
+        for native in (True, False):
+            f = TandemRepeatFinder("/dev/null")
+            f._NATIVE_WALK = native
+            f.sequences = {"c": text}
+            recs.append(f._recompute_repeat("c", 0, len(text), 4))
+        assert recs[0] == recs[1]
+
+
+def test_recompute_repeat_native_and_python_walks_agree():
+    rng = np.random.default_rng(29)
+    pieces = []
+    spans = []
+    pos = 0
+    for i in range(400):
+        gap = "".join("ACGTN"[x] for x in rng.integers(0, 5, int(rng.integers(0, 30))))
+        k = int(rng.choice([1, 2, 3, 4, 5, 6, 8, 11, 16, 40]))
+        _, body = _mutated_tandem(rng, k, int(rng.integers(2, 25)), float(rng.choice([0.0, 0.05, 0.2])))
+        pieces += [gap, body]
+        pos += len(gap)
+        spans.append((pos, pos + len(body), k))
+        pos += len(body)
+    seq = "".join(pieces)
+    on, off = TandemRepeatFinder("/dev/null"), TandemRepeatFinder("/dev/null")
+    off._NATIVE_WALK = False
+    on.sequences = off.sequences = {"c": seq}
+    imperfect = 0
+    for a, b, k in spans:
+        for kk in (k, max(1, k - 1), 2 * k):
+            got, want = on._recompute_repeat("c", a, b, kk, tier_hint=2), off._recompute_repeat("c", a, b, kk, tier_hint=2)
+            assert got == want, (a, b, kk)
+            imperfect += bool(want.variations)
+    assert imperfect > 100
+
+
 def test_merge_hands_over_the_union_record():
     """_merge_adjacent_repeats re-uses the union derived by _should_merge_repeats when the
     arguments coincide; same merged records as two independent derivations."""
