@@ -130,9 +130,21 @@ def _process_and_finish_contig(args):
     n_raw = 0 if rows is None else len(rows)
     if not n_raw:
         return [], 0, 0, 0
+    return _finish_contig_rows((chrom, seq, config, left, right, rows, text_arr))
+
+
+def _finish_contig_rows(args):
+    """The host half of the per-contig path: this contig's share of the post-processing chain on the detector's
+    rows.  CPU only (NumPy + the host functions of libbwtk.so), so it can run in a pool of plain worker processes
+    while the parent keeps the GPU busy with the next contig.  `seq` may be None for an ASCII contig: it is the
+    text without its sentinel."""
+    chrom, seq, config, left, right, rows, text_arr = args
+    n_raw = len(rows)
     try:
         from . import rowchain
 
+        if seq is None:
+            seq = text_arr[:-1].tobytes().decode("ascii")
         return rowchain.finish_rows(_contig_finder(chrom, seq, config, left, right), chrom, text_arr, rows)
     except Exception as exc:  # same policy as the detection worker
         print(f"ERROR post-processing chromosome {chrom}: {exc}")
@@ -140,6 +152,54 @@ def _process_and_finish_contig(args):
 
         traceback.print_exc()
         return [], n_raw, n_raw, n_raw
+
+
+# The chain pool (one GPU, several contigs): from this many bases on, the contigs' chains go to CPU worker
+# processes; below it starting the workers costs more than the chains.  Tests set it to 0.
+CHAIN_POOL_MIN_BASES = 4_000_000
+
+
+def _chain_pool_size(tasks: List[Tuple], n_jobs: int) -> int:
+    """Worker processes for the post-processing chains of `tasks` when detection stays in this process."""
+    if len(tasks) < 2 or (n_jobs or 1) < 2 or sum(len(t[1]) for t in tasks) < CHAIN_POOL_MIN_BASES:
+        return 0
+    return max(1, min(int(n_jobs), len(tasks), cpu_count()))
+
+
+def _run_with_chain_pool(tasks: List[Tuple], procs: int):
+    """Per-contig path on ONE GPU: detection (index build + strict scan, milliseconds per contig) runs here, contig
+    after contig, longest first; every contig's rows go to a pool of `procs` CPU processes for the chain, which is
+    what a contig's time consists of (seconds per contig).  Yields what _process_and_finish_contig returns, in
+    any order.  The reference does the same split the other way round -- its pool workers do everything
+    (bwt.py:3863-3899) -- because there the detection is the expensive half."""
+    import multiprocessing as mp
+
+    import numpy as np
+
+    ctx = mp.get_context("spawn")          # the parent holds a CUDA context: workers must not be forked from it
+    with ctx.Pool(procs) as pool:
+        pending = []
+        for chrom, seq, config, left, right in sorted(tasks, key=lambda t: -len(t[1])):
+            try:
+                rows, text_arr = _detect_rows(chrom, seq, config)
+            except Exception as exc:  # the reference swallows worker failures the same way
+                print(f"ERROR processing chromosome {chrom}: {exc}")
+                import traceback
+
+                traceback.print_exc()
+                yield [], 0, 0, 0
+                continue
+            if rows is None or not len(rows):
+                yield [], 0, 0, 0
+                continue
+            # the chain reads (start, end, primitive period, copies); an ASCII contig is rebuilt from its text
+            payload = (chrom, None if seq.isascii() else seq, config, left, right,
+                       np.ascontiguousarray(rows[:, :4]), text_arr)
+            pending.append(pool.apply_async(_finish_contig_rows, (payload,)))
+            while pending and pending[0].ready():
+                yield pending.pop(0).get()
+        for res in pending:
+            yield res.get()
 
 
 # consensus motif -> (strand, composition, entropy) for _recompute_repeat (pure functions of the string)
@@ -417,7 +477,11 @@ class TandemRepeatFinder:
         if per_contig:
             finished: List[TandemRepeat] = []
             n_raw = n_kept = n_unique = 0
-            for part, a, b, c in sharding.run_tasks(_process_and_finish_contig, self._finish_tasks(tasks), n_jobs):
+            ftasks = self._finish_tasks(tasks)
+            pool_procs = 0 if sharding.worker_processes(len(ftasks), n_jobs) > 1 else _chain_pool_size(ftasks, n_jobs)
+            results = (_run_with_chain_pool(ftasks, pool_procs) if pool_procs
+                       else sharding.run_tasks(_process_and_finish_contig, ftasks, n_jobs))
+            for part, a, b, c in results:
                 finished.extend(part)
                 n_raw, n_kept, n_unique = n_raw + a, n_kept + b, n_unique + c
                 done += 1

@@ -84,6 +84,28 @@ def test_cli_byte_identical_on_gpu(tmp_path, capsys, fa, flags, tag, jobs):
 
 
 @pytest.mark.gpu
+def test_cli_chain_pool_on_gpu(tmp_path, capsys, monkeypatch):
+    """Several contigs on one GPU with --jobs 4: detection in this process (CUDA context up), every contig's
+    chain in a spawned CPU worker (pipeline._run_with_chain_pool, forced on for a small FASTA).  Byte-identical
+    output; the pool path really ran."""
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200 import bwt, pipeline, sharding
+
+    fa, flags, tag = next(c for c in CASES if c[0] == "test2.fa" and "--tier1" not in c[1])
+    monkeypatch.setattr(pipeline, "CHAIN_POOL_MIN_BASES", 0)
+    monkeypatch.setattr(sharding, "worker_processes", lambda n_tasks, n_jobs: 1)
+    used = []
+    real = pipeline._run_with_chain_pool
+    monkeypatch.setattr(pipeline, "_run_with_chain_pool", lambda tasks, procs: used.append(procs) or real(tasks, procs))
+    for fmt in ("bed", "strfinder"):
+        out = tmp_path / f"{tag}.{fmt}"
+        bwt.main([os.path.join(CLI, fa), "-o", str(out), "--format", fmt, "--jobs", "4"] + flags)
+        assert out.read_text() == _expected(tag, fmt), f"{tag} ({fmt}, chain pool) differs"
+    assert used and all(p >= 2 for p in used)
+    capsys.readouterr()
+
+
+@pytest.mark.gpu
 def test_reference_unit_tests_on_gpu():
     """The reference's own assertions (tests/test_repeat_outputs.py:36-62) through the drop-in."""
     import bwt_algorithm_b200  # noqa: F401

@@ -445,6 +445,52 @@ def test_drivers_use_the_row_chain_and_match_the_object_chain(oracle, monkeypatc
     assert recs and all(isinstance(r, finders.TandemRepeat) for r in recs)
 
 
+def test_chain_pool_finishes_contigs_in_cpu_workers(oracle, monkeypatch, capsys):
+    """One GPU, several contigs, --jobs > 1: detection stays in the parent, every contig's chain runs in a spawned
+    CPU worker (pipeline._run_with_chain_pool).  Same calls and summary lines as the in-process path."""
+    import dataclasses
+    import os
+
+    from bwt_algorithm_b200 import pipeline, sharding
+
+    def fake_rows(chrom, seq, config):
+        text = (seq + "$").encode()
+        rows = oracle.strict_scan(text, 1, max(config["max_unit_len"], min(len(seq) // config["min_copies"], 1000)),
+                                  0, config["min_copies"])
+        return rows, np.frombuffer(text, np.uint8)
+
+    monkeypatch.setattr(pipeline, "_detect_rows", fake_rows)
+    monkeypatch.setattr(sharding, "worker_processes", lambda n_tasks, n_jobs: 1)
+    fixture = os.path.join(os.path.dirname(__file__), "golden", "cli", "test2.fa")
+    outs = []
+    for min_bases, jobs in ((1 << 40, 3), (0, 3), (0, 1)):
+        monkeypatch.setattr(pipeline, "CHAIN_POOL_MIN_BASES", min_bases)
+        finder = TandemRepeatFinder(fixture)
+        seqs = finder.load_reference()
+        assert len(seqs) >= 2
+        tasks = finder._finish_tasks([(c, q, finder._config(False, True)) for c, q in seqs.items()])
+        assert pipeline._chain_pool_size(tasks, jobs) == (min(jobs, len(seqs)) if min_bases == 0 and jobs > 1 else 0)
+        final = finder.find_tandem_repeats_parallel(enable_tier1=False, enable_tier2=True, n_jobs=jobs)
+        lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith(("Nested call", "Analysis complete"))]
+        outs.append(([dataclasses.astuple(r) for r in final], lines))
+    assert outs[0][0] and outs[0] == outs[1] == outs[2]
+    # a contig whose detection fails is reported and skipped, the others are finished (bwt.py:3134-3141)
+    monkeypatch.setattr(pipeline, "CHAIN_POOL_MIN_BASES", 0)
+    first = next(iter(seqs))
+
+    def flaky(chrom, seq, config):
+        if chrom == first:
+            raise RuntimeError("boom")
+        return fake_rows(chrom, seq, config)
+
+    monkeypatch.setattr(pipeline, "_detect_rows", flaky)
+    finder = TandemRepeatFinder(fixture)
+    finder.load_reference()
+    final = finder.find_tandem_repeats_parallel(enable_tier1=False, enable_tier2=True, n_jobs=3)
+    assert f"ERROR processing chromosome {first}: boom" in capsys.readouterr().out
+    assert [dataclasses.astuple(r) for r in final] == [t for t in outs[0][0] if t[0] != first]
+
+
 def test_row_chain_homopolymer_shortcut_equals_generic_path():
     """rowchain.finish_rows settles isolated homopolymer merge events on integers (FAST_K1); with the shortcut
     off every candidate goes through _should_merge_repeats / _recompute_repeat.  Same calls either way, on

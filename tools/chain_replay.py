@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--contigs", type=int, default=1)
+    ap.add_argument("--jobs", type=int, default=4)
     ap.add_argument("--limit", type=int, default=0, help="use only the first N bases (rows entirely inside)")
     args = ap.parse_args()
     import numpy as np
@@ -47,23 +49,35 @@ def main():
         n = args.limit
         s = s[:n]
         rows = rows[rows[:, 1] + rows[:, 6] < n]      # the run that made the call ends before the cut
-    text = np.concatenate([s, np.frombuffer(b"$", np.uint8)])
+    # --contigs C: the contig cut into C pieces (calls that cross a cut are dropped): timing of the chain pool only
+    C = max(1, args.contigs)
+    cuts = [n * i // C for i in range(C + 1)]
+    served = {}
+    for i in range(C):
+        a, b = cuts[i], cuts[i + 1]
+        sel = rows[(rows[:, 0] >= a) & (rows[:, 1] + rows[:, 6] < b)].copy() if C > 1 else rows
+        sel[:, 0] -= a
+        sel[:, 1] -= a
+        served[f"chr21_sized_{i}" if C > 1 else "chr21_sized"] = (sel, np.concatenate([s[a:b], np.frombuffer(b"$", np.uint8)]))
 
     def replay_rows(chrom, seq, config):
-        assert len(seq) == n
+        r, text = served[chrom]
+        assert len(seq) + 1 == len(text)
         if config.get("show_progress"):
-            print(f"  [{chrom}] Strict adjacency: {len(rows)} tandem repeats detected")
-        return rows.copy(), text.copy()
+            print(f"  [{chrom}] Strict adjacency: {len(r)} tandem repeats detected")
+        return r.copy(), text.copy()
 
     pipeline._detect_rows = replay_rows
     tmp = tempfile.mkdtemp(prefix="bwtk_replay_")
     fa, out = os.path.join(tmp, "chr21_sized.fa"), os.path.join(tmp, "out." + args.format)
-    pad = (-s.size) % 80
-    body = np.concatenate([s, np.full(pad, 10, np.uint8)]).reshape(-1, 80)
-    lines = np.concatenate([body, np.full((body.shape[0], 1), 10, np.uint8)], axis=1).tobytes()
     with open(fa, "wb") as fh:
-        fh.write(b">chr21_sized synthetic\n" + lines.rstrip(b"\n") + b"\n")
-    argv = [fa, "--progress", "--format", args.format, "--jobs", "4", "--flank-trim", "0", "-o", out]
+        for name, (_, text) in served.items():
+            part = text[:-1]
+            pad = (-part.size) % 80
+            body = np.concatenate([part, np.full(pad, 10, np.uint8)]).reshape(-1, 80)
+            lines = np.concatenate([body, np.full((body.shape[0], 1), 10, np.uint8)], axis=1).tobytes()
+            fh.write(b">" + name.encode() + b" synthetic\n" + lines.rstrip(b"\n") + b"\n")
+    argv = [fa, "--progress", "--format", args.format, "--jobs", str(args.jobs), "--flank-trim", "0", "-o", out]
     walls = []
     for _ in range(args.repeat):
         t0 = time.perf_counter()
