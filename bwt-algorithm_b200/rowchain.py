@@ -42,6 +42,18 @@ for _c, _v in ((65, 0), (84, 0), (67, 1), (71, 1)):
     _AT[_c] = _v
 
 
+class _RowCall:
+    """What the merge predicates read of an exact strict-scan call (TandemRepeatFinder._should_merge_repeats /
+    _merge_repeats: chrom, motif, span, tier, mismatch rate), without the record around it: four out of five
+    rows that reach a merge test are absorbed by the union and never become records."""
+    __slots__ = ("chrom", "start", "end", "motif", "consensus_motif", "tier", "mismatch_rate")
+
+    def __init__(self, chrom, start, end, motif):
+        self.chrom, self.start, self.end = chrom, start, end
+        self.motif = self.consensus_motif = motif
+        self.tier, self.mismatch_rate = 2, 0.0
+
+
 def suppress_rows(rows: np.ndarray, overlap_threshold: float = 0.5) -> np.ndarray:
     """Boolean keep mask of ``_suppress_nested_short_calls`` for the exact calls of one contig."""
     n = int(rows.shape[0])
@@ -100,6 +112,10 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
 
     def make_row(i: int) -> TandemRepeat:
         return maker(int(S[i]), int(E[i]), int(K[i]), int(Cn[i]))
+
+    def light_row(i: int) -> _RowCall:
+        s0 = int(S[i])
+        return _RowCall(chrom, s0, int(E[i]), text_bytes[s0:s0 + int(K[i])].decode("ascii", errors="replace"))
 
     # ---- 3. merge adjacent.  link[i]: rows i and i+1 pass the cheap (necessary) tests of _should_merge_repeats
     link = np.zeros(m, bool)
@@ -221,7 +237,7 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
                     STATS["requeued"] += 1
                 continue
             # fall through: redo this candidate on records (rows released above stay released)
-        cur = make_row(e)
+        cur = light_row(e)
         j = e + 1
         touched = False
         while j < m:
@@ -231,7 +247,7 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
             if vrun[j] > 0:                              # a settled homopolymer event is reached after all:
                 vrun[j] = 0                              # it never happened -- its rows are ordinary rows again
                 alive[j + 1] = True
-            nxt_rec = make_row(j)
+            nxt_rec = light_row(j)
             if finder._should_merge_repeats(cur, nxt_rec):
                 cur = finder._merge_repeats(cur, nxt_rec)
                 touched = True

@@ -78,15 +78,16 @@ def main():
             lines = np.concatenate([body, np.full((body.shape[0], 1), 10, np.uint8)], axis=1).tobytes()
             fh.write(b">" + name.encode() + b" synthetic\n" + lines.rstrip(b"\n") + b"\n")
     argv = [fa, "--progress", "--format", args.format, "--jobs", str(args.jobs), "--flank-trim", "0", "-o", out]
-    walls = []
+    walls, cpus = [], []
     for _ in range(args.repeat):
-        t0 = time.perf_counter()
+        t0, c0 = time.perf_counter(), time.process_time()
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
             bwt.main(argv)
         walls.append(round(time.perf_counter() - t0, 2))
+        cpus.append(round(time.process_time() - c0, 2))
     tail = [ln for ln in buf.getvalue().splitlines() if "Nested call" in ln or "Completed" in ln]
-    print(json.dumps({"bases": n, "rows": int(len(rows)), "wall_s": walls, "output_lines": sum(1 for _ in open(out)),
+    print(json.dumps({"bases": n, "rows": int(len(rows)), "wall_s": walls, "cpu_s": cpus, "output_lines": sum(1 for _ in open(out)),
                       "md5": hashlib.md5(open(out, "rb").read()).hexdigest(), "stdout": tail}))
     if args.profile:
         pr = cProfile.Profile()
