@@ -156,7 +156,7 @@ def _finish_contig_rows(args):
 
 # The chain pool (one GPU, several contigs): from this many bases on, the contigs' chains go to CPU worker
 # processes; below it starting the workers costs more than the chains.  Tests set it to 0.
-CHAIN_POOL_MIN_BASES = 4_000_000
+CHAIN_POOL_MIN_BASES = 16_000_000
 
 
 def _chain_pool_size(tasks: List[Tuple], n_jobs: int) -> int:

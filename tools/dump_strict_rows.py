@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=46_709_983)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "strict_rows_chr21.npz"))
+    ap.add_argument("--compare", default="", help="an earlier dump: only report whether the rows are the same")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -38,6 +39,12 @@ def main():
         rows = detect.strict_rows(d, 1, unit_cap, 0, 3)
         ms.append(round((time.perf_counter() - t0) * 1e3, 2))
     assert not rows[:, [4, 5, 7]].any()
+    if args.compare:
+        z = np.load(args.compare)
+        same = (int(z["n"]) == args.n and len(z["start"]) == len(rows)
+                and all(np.array_equal(z[k], rows[:, c]) for k, c in (("start", 0), ("end", 1), ("prim", 2), ("copies", 3), ("unit", 6))))
+        print(json.dumps({"rows": int(len(rows)), "strict_rows_ms": ms, "same_as": args.compare, "same": bool(same)}))
+        sys.exit(0 if same else 1)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     np.savez_compressed(args.out, start=rows[:, 0], end=rows[:, 1], prim=rows[:, 2].astype(np.int16),
                         copies=rows[:, 3], unit=rows[:, 6].astype(np.int16), n=np.int64(args.n))
