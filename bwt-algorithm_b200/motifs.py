@@ -525,7 +525,7 @@ def align_region_native(seq_bytes: bytes, start: int, end: int, template: bytes,
         _CONS_BUF = C.create_string_buffer(2 * k)
     cons, out = _CONS_BUF, _OUT_BUF
     while True:
-        rc = _NATIVE_WALK(seq_bytes, len(seq_bytes), start, end, template, k, tol, max_indel, min_copies,
+        rc = _NATIVE_WALK(seq_bytes, len(seq_bytes), int(start), int(end), template, k, tol, max_indel, int(min_copies),
                           cons, out, _NOTES_BUF, len(_NOTES_BUF))
         if rc == -4:                                     # BWTK_EOVERFLOW: the notes need a larger buffer
             _NOTES_BUF = C.create_string_buffer(int(out[7]) * 2)
