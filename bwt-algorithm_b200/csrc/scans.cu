@@ -564,42 +564,53 @@ struct Resolved {
 // Replays the greedy walk over the sorted candidate runs of one unit length:
 // entry e = max(run start, end of the previous emission); emit when
 // e <= run_end - (mc-1)*u; the array then ends at e + u*(1 + (run_end-e)/u).
+// A run only depends on the run before it when that one's array can reach past its start
+// (start < previous run end + u); runs linked that way form a chain.  The thread of the chain's FIRST run walks
+// the chain forward once and leaves (entry, copies) for every member -- O(chain) in total, where every
+// member walking back to the head on its own would be O(chain^2) on texts that are one long chain (a period-2
+// text with a mismatch every few bases).  Chains of ordinary sequence have one or two members.
 __global__ void __launch_bounds__(256)
-    resolve_kernel(const uint8_t *__restrict__ text, const unsigned long long *__restrict__ key,
-                   const uint32_t *__restrict__ val, int64_t m, int abits, int64_t umax, int64_t mc,
-                   Resolved res)
+    resolve_walk_kernel(const unsigned long long *__restrict__ key, const uint32_t *__restrict__ val, int64_t m,
+                        int abits, int64_t umax, int64_t mc, Resolved res)
 {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
     const unsigned long long amask = (1ull << abits) - 1ull;
-    const unsigned long long kt = key[t];
-    const int64_t urev = (int64_t)(kt >> abits);
+    const int64_t urev = (int64_t)(key[t] >> abits);
     const int64_t u = umax - urev;
     const int64_t L = (mc - 1) * u;
-    // walk back while the previous run of the same unit can still reach this one
-    int64_t s = t;
-    while (s > 0) {
-        unsigned long long kp = key[s - 1];
-        if ((int64_t)(kp >> abits) != urev) break;
-        int64_t a_s = (int64_t)(key[s] & amask);
-        int64_t b_p = (int64_t)val[s - 1];
-        if (a_s >= b_p + u) break;
-        s--;
-    }
-    int64_t prev_end = -1, e = 0, cnt = 0;
-    bool emitted = false;
-    for (int64_t r = s; r <= t; r++) {
-        int64_t a = (int64_t)(key[r] & amask), b = (int64_t)val[r];
-        e = a > prev_end ? a : prev_end;
-        emitted = e <= b - L;
+    if (t > 0 && (int64_t)(key[t - 1] >> abits) == urev && (int64_t)(key[t] & amask) < (int64_t)val[t - 1] + u)
+        return;                                  // not the first run of its chain
+    int64_t prev_end = -1, prev_b = 0;
+    for (int64_t r = t; r < m; r++) {
+        const unsigned long long kr = key[r];
+        const int64_t a = (int64_t)(kr & amask), b = (int64_t)val[r];
+        if (r > t && ((int64_t)(kr >> abits) != urev || a >= prev_b + u)) break;      // the chain ends
+        const int64_t e = a > prev_end ? a : prev_end;
+        const bool emitted = e <= b - L;
+        res.emit[r] = emitted ? 1 : 0;
         if (emitted) {
-            cnt = 1 + (b - e) / u;
+            const int64_t cnt = 1 + (b - e) / u;
             prev_end = e + cnt * u;
+            int32_t *row = res.row + r * BWTK_REC_W;
+            row[0] = (int32_t)e;
+            row[3] = (int32_t)cnt;
         }
+        prev_b = b;
     }
-    res.emit[t] = emitted ? 1 : 0;
-    if (!emitted) return;
-    // primitive period of the first unit (MotifUtils.smallest_period_str, bwt.py:1124-1133)
+}
+
+// The record of every emitted run: primitive period of the first unit (MotifUtils.smallest_period_str,
+// bwt.py:1124-1133), span, copies.  One thread per run; (entry, copies) come from resolve_walk_kernel.
+__global__ void __launch_bounds__(256)
+    resolve_rows_kernel(const uint8_t *__restrict__ text, const unsigned long long *__restrict__ key, int64_t m,
+                        int abits, int64_t umax, Resolved res)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m || !res.emit[t]) return;
+    const int64_t u = umax - (int64_t)(key[t] >> abits);
+    int32_t *row = res.row + t * BWTK_REC_W;
+    const int64_t e = row[0], cnt = row[3];
     int64_t prim = u;
     for (int64_t p = 1; p <= u / 2; p++) {
         if (u % p) continue;
@@ -608,9 +619,8 @@ __global__ void __launch_bounds__(256)
             if (__ldg(text + e + j) != __ldg(text + e + j - p)) { ok = false; break; }
         if (ok) { prim = p; break; }
     }
-    int64_t end = e + cnt * u;
-    int32_t *row = res.row + t * BWTK_REC_W;
-    row[0] = (int32_t)e; row[1] = (int32_t)end; row[2] = (int32_t)prim;
+    const int64_t end = e + cnt * u;
+    row[1] = (int32_t)end; row[2] = (int32_t)prim;
     row[3] = (int32_t)(prim < u ? (end - e) / prim : cnt);
     row[4] = 0; row[5] = 0; row[6] = (int32_t)u; row[7] = 0;
 }
@@ -1638,8 +1648,9 @@ extern "C" int32_t bwtk_strict_scan_hinted(const uint8_t *d_text, int64_t n_tota
     if (m == 0) return BWTK_OK;
     const int abits_runs = strict::bits_for(n);
     strict::Resolved res{emit, rows};
-    strict::resolve_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(d_text, sk, sv, m, abits_runs, umax,
-                                                                      min_copies, res);
+    strict::resolve_walk_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(sk, sv, m, abits_runs, umax, min_copies, res);
+    BWTK_LAUNCH_CHECK();
+    strict::resolve_rows_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(d_text, sk, m, abits_runs, umax, res);
     BWTK_LAUNCH_CHECK();
     strict::CountEmit ce{emit};
     strict::WriteRows wr{rows, d_rec, cap};

@@ -60,6 +60,31 @@ def test_strict_rows_other_params(detect, oracle, params):
     assert np.array_equal(got, want)
 
 
+def test_strict_rows_on_one_long_chain_of_runs(detect, oracle):
+    """Two motif variants that differ in one base, alternating every few copies: every switch costs the unit-3 match
+    run one position, so all candidate runs of that unit are linked (each starts within a unit of the end of the run
+    before) and every entry depends on the emission before it (the reference's `i = end` jump).  The replay walks
+    the chain once from its first run: rows equal the oracle's, and 6 Mb of the same text -- one chain of 10^6 runs,
+    on which a walk back from every run would be quadratic -- finishes in a moment."""
+    import time
+
+    def chain_text(n, reps):
+        blk = b"AAC" * reps + b"AAG" * reps
+        return (blk * (n // len(blk) + 1))[:n] + b"$"
+
+    for reps, params in ((2, (1, 12, 0, 2)), (3, (1, 9, 0, 3)), (2, (2, 7, 0, 2)), (4, (1, 30, 0, 3))):
+        text = chain_text(30_000, reps)
+        want = oracle.strict_scan(text, *params)
+        got = detect.strict_rows(text, *params)
+        assert np.array_equal(got, want), (reps, params)
+        assert len(want) > 1000
+    big = chain_text(6_000_000, 2)
+    detect.strict_rows(big, 2, 12, 0, 2)
+    t0 = time.perf_counter()
+    rows = detect.strict_rows(big, 2, 12, 0, 2)
+    assert time.perf_counter() - t0 < 2.0 and len(rows) > 900_000
+
+
 def test_strict_rows_150k(detect, oracle):
     text = gen_contig(150_000, 42).tobytes() + b"$"
     want = oracle.strict_scan(text, 1, 1000, 0, 3)
