@@ -13,6 +13,7 @@ from __future__ import annotations
 import functools
 import math
 import operator
+import threading
 from collections import Counter
 from typing import Dict, Iterator, List, Optional, Tuple
 
@@ -484,8 +485,21 @@ def _align_unit_cached(motif: str, window: str, max_indel: int, mismatch_toleran
 
 
 # ---- native copy-by-copy walk (csrc/rowchain.cu: bwtk_align_repeat_region) ---------------------------------
-_NOTES_BUF = _CONS_BUF = _OUT_BUF = None
 _NATIVE_WALK = None      # False once the library turned out to be unavailable
+
+
+class _WalkBuffers(threading.local):
+    """Output buffers of the native walk, one set per thread (ctypes releases the GIL during the call)."""
+
+    def __init__(self):
+        import ctypes as C
+
+        self.notes = C.create_string_buffer(1 << 12)
+        self.cons = C.create_string_buffer(1 << 10)
+        self.out = (C.c_int64 * 8)()
+
+
+_WALK_BUFFERS = None
 
 
 def align_region_native(seq_bytes: bytes, start: int, end: int, template: bytes, mismatch_fraction: float = 0.1,
@@ -497,7 +511,7 @@ def align_region_native(seq_bytes: bytes, start: int, end: int, template: bytes,
     returns None, or ``NotImplemented`` when the native walk does not apply (library missing, a consensus
     column with more than 8 distinct symbols): the caller then runs the Python walk, which defines the
     behaviour (tests/test_host_glue_cpu.py holds the two equal on random and planted sequences)."""
-    global _NOTES_BUF, _CONS_BUF, _OUT_BUF, _NATIVE_WALK
+    global _NATIVE_WALK, _WALK_BUFFERS
     import ctypes as C
 
     if _NATIVE_WALK is False:
@@ -506,13 +520,12 @@ def align_region_native(seq_bytes: bytes, start: int, end: int, template: bytes,
         from . import _lib
 
         try:
-            _NATIVE_WALK = _lib.lib().bwtk_align_repeat_region
+            walk = _lib.lib().bwtk_align_repeat_region
         except Exception:
             _NATIVE_WALK = False
             return NotImplemented
-        _NOTES_BUF = C.create_string_buffer(1 << 12)
-        _CONS_BUF = C.create_string_buffer(1 << 10)
-        _OUT_BUF = (C.c_int64 * 8)()
+        _WALK_BUFFERS = _WalkBuffers()
+        _NATIVE_WALK = walk
     k = len(template)
     if k == 0 or not seq_bytes:
         return None
@@ -521,14 +534,15 @@ def align_region_native(seq_bytes: bytes, start: int, end: int, template: bytes,
         max_indel = max(1, min(10, k // 2 if k >= 4 else 1))
     else:
         max_indel = max(0, max_indel)
-    if k > len(_CONS_BUF):
-        _CONS_BUF = C.create_string_buffer(2 * k)
-    cons, out = _CONS_BUF, _OUT_BUF
+    buf = _WALK_BUFFERS
+    if k > len(buf.cons):
+        buf.cons = C.create_string_buffer(2 * k)
+    cons, out = buf.cons, buf.out
     while True:
         rc = _NATIVE_WALK(seq_bytes, len(seq_bytes), int(start), int(end), template, k, tol, max_indel, int(min_copies),
-                          cons, out, _NOTES_BUF, len(_NOTES_BUF))
+                          cons, out, buf.notes, len(buf.notes))
         if rc == -4:                                     # BWTK_EOVERFLOW: the notes need a larger buffer
-            _NOTES_BUF = C.create_string_buffer(int(out[7]) * 2)
+            buf.notes = C.create_string_buffer(int(out[7]) * 2)
             continue
         break
     if rc == 0:
@@ -537,6 +551,6 @@ def align_region_native(seq_bytes: bytes, start: int, end: int, template: bytes,
         return NotImplemented
     copies, consumed, errs, worst, n_ins, n_del, n_notes, note_bytes = out
     denom = copies * k
-    notes = _NOTES_BUF.raw[:note_bytes].decode("ascii").split("\n") if n_notes else []
+    notes = buf.notes.raw[:note_bytes].decode("ascii").split("\n") if n_notes else []
     return (cons.raw[:k].decode("ascii"), copies, consumed, (errs / denom if denom > 0 else 0.0), worst, notes,
             n_ins, n_del)
