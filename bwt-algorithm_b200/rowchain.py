@@ -405,10 +405,14 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
         out.append(((r.start, r.end, q), r))
     if not out:
         return made, n_raw, n_kept, n_unique
-    keyed = [((int(kS[q]), int(kE[q]), int(q)), r) for q, r in zip(plain.tolist(), made)]
-    keyed += out
-    keyed.sort(key=lambda kr: kr[0])
-    return [r for _, r in keyed], n_raw, n_kept, n_unique
+    # sort by (start, end, list position): the survivors made from rows are in that order already, the others
+    # (merged, collapsed and virtual calls) are filed among them
+    o_keys = np.array([k for k, _ in out], np.int64).reshape(-1, 3)
+    s_all = np.concatenate((kS[plain], o_keys[:, 0]))
+    e_all = np.concatenate((kE[plain], o_keys[:, 1]))
+    q_all = np.concatenate((plain, o_keys[:, 2]))
+    every = made + [r for _, r in out]
+    return [every[i] for i in np.lexsort((q_all, e_all, s_all)).tolist()], n_raw, n_kept, n_unique
 
 
 def _finish_rows_slow(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray):
