@@ -47,6 +47,11 @@ _SIGS = {
     "bwtk_profile_report": (_i32, [C.c_char_p, _i32]),
     "bwtk_upload_text": (_i32, [_p, _p, _i64, _p]),
     "bwtk_download": (_i32, [_p, _p, _i64, _p]),
+    "bwtk_device_count": (_i32, [_p]),
+    "bwtk_dev_alloc": (_i32, [_p, _i64]),
+    "bwtk_dev_free": (_i32, [_p]),
+    "bwtk_copy_to_device": (_i32, [_p, _p, _i64, _p]),
+    "bwtk_copy_to_host": (_i32, [_p, _p, _i64, _p]),
     "bwtk_fasta_index": (_i32, [_p, _i64, _p, _i64, _p, _p]),
     "bwtk_fasta_sequence": (_i64, [_p, _i64, _i64, _i64, _i64, _i32, _p]),
     "bwtk_suppress_nested": (_i32, [_p, _p, _p, _p, _i64, C.c_double, _p]),

@@ -484,6 +484,55 @@ static __global__ void __launch_bounds__(256)
     if (t < tail) dst[head + vecs * 16 + t] = src[head + vecs * 16 + t];
 }
 
+// ---- device memory for hosts that bring no CUDA allocator of their own (the CLI's start-up path: a fresh
+// `python bwt.py` answers a small FASTA before `import torch` would have finished) ------------------------------
+extern "C" int32_t bwtk_device_count(int32_t *count)
+{
+    BWTK_REQUIRE(count, "null pointer");
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();          // no driver / no device is an answer (0), not a sticky error
+        n = 0;
+    }
+    *count = n;
+    return BWTK_OK;
+}
+
+extern "C" int32_t bwtk_dev_alloc(void **d_ptr, int64_t bytes)
+{
+    BWTK_REQUIRE(d_ptr && bytes >= 0, "bad arguments");
+    *d_ptr = nullptr;
+    BWTK_CUDA(cudaMalloc(d_ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return BWTK_OK;
+}
+
+extern "C" int32_t bwtk_dev_free(void *d_ptr)
+{
+    if (d_ptr) BWTK_CUDA(cudaFree(d_ptr));
+    return BWTK_OK;
+}
+
+extern "C" int32_t bwtk_copy_to_device(void *d_dst, const void *h_src, int64_t bytes, void *stream)
+{
+    if (bytes <= 0) return BWTK_OK;
+    BWTK_REQUIRE(d_dst && h_src, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    BWTK_CUDA(cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    return BWTK_OK;
+}
+
+extern "C" int32_t bwtk_copy_to_host(void *h_dst, const void *d_src, int64_t bytes, void *stream)
+{
+    if (bytes <= 0) return BWTK_OK;
+    BWTK_REQUIRE(h_dst && d_src, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    BWTK_CUDA(cudaMemcpyAsync(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, st));
+    BWTK_CUDA(cudaStreamSynchronize(st));
+    return BWTK_OK;
+}
+
 extern "C" int32_t bwtk_download(const void *d_src, void *h_pinned, int64_t bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;

@@ -38,15 +38,30 @@ def _detect_rows(chrom: str, seq: str, config: dict):
     (rows int32[R, 8] or None when no detector ran, text_arr uint8 incl. '$', max_mismatch)."""
     import numpy as np
 
-    from . import detect
-    from .finders import _device_text_of
+    from . import lean
 
-    pinned = _PINNED.get(chrom)
-    if pinned is not None and pinned.numel() != len(seq) + 1:
-        pinned = None                      # a different contig of the same name
-    core = BWTCore(seq + "$", config["sa_sample_rate"], _pinned_text=pinned)
     verbose = config.get("show_progress", False)
     rows = None
+    core = None
+    # A fresh CLI process in which nobody has imported torch yet: the strict scan runs on buffers of the library's own
+    # (lean.py) -- same kernels, same rows, seconds of start-up saved.  Otherwise the index object and torch's allocator.
+    if lean.enabled() and seq.isascii() and lean.device_count() > 0:
+        text_arr = np.frombuffer((seq + "$").encode("ascii"), np.uint8)
+
+        def scan(unit_cap, min_copies):
+            return lean.strict_rows(text_arr, 1, unit_cap, 0, min_copies)
+    else:
+        from . import detect
+        from .finders import _device_text_of
+
+        pinned = _PINNED.get(chrom)
+        if pinned is not None and pinned.numel() != len(seq) + 1:
+            pinned = None                      # a different contig of the same name
+        core = BWTCore(seq + "$", config["sa_sample_rate"], _pinned_text=pinned)
+        text_arr = core.text_arr
+
+        def scan(unit_cap, min_copies):
+            return detect.strict_rows(_device_text_of(core), 1, unit_cap, 0, min_copies)
     try:
         if verbose:
             print(f"  [{chrom}] Building indices ({len(seq):,} bp)...")
@@ -56,12 +71,13 @@ def _detect_rows(chrom: str, seq: str, config: dict):
             else:
                 min_copies = config["min_copies"]
                 unit_cap = max(config["max_unit_len"], min(len(seq) // min_copies, 1000))
-                rows = detect.strict_rows(_device_text_of(core), 1, unit_cap, 0, min_copies)
+                rows = scan(unit_cap, min_copies)
                 if verbose:
                     print(f"  [{chrom}] Strict adjacency: {len(rows)} tandem repeats detected")
-        text_arr = np.array(core.text_arr, copy=True) if rows is not None and len(rows) else None
+        text_arr = np.array(text_arr, copy=True) if rows is not None and len(rows) else None
     finally:
-        core.clear()
+        if core is not None:
+            core.clear()
     return rows, text_arr
 
 
@@ -212,6 +228,12 @@ _PINNED: Dict[str, object] = {}
 
 
 def _pinning_enabled() -> bool:
+    """Pinned staging of the contigs pays when torch's allocator is in play; a process that has not imported torch
+    (the CLI's start-up path, lean.py) uploads from ordinary memory and does not import it for this."""
+    import sys
+
+    if "torch" not in sys.modules:
+        return False
     try:
         import torch
 

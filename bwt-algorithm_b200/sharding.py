@@ -29,6 +29,13 @@ def lpt_partition(lengths: Sequence[int], nbins: int) -> List[List[int]]:
 
 
 def _gpu_count() -> int:
+    import sys
+
+    if "torch" not in sys.modules:            # the CLI's start-up path (lean.py): ask the library, not torch
+        from . import lean
+
+        if lean.enabled():
+            return lean.device_count()
     try:
         import torch
 

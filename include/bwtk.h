@@ -64,6 +64,19 @@ int32_t bwtk_upload_text(const uint8_t *h_pinned, uint8_t *d_dst, int64_t n, voi
  * over PCIe, for the same reason.  Both pointers 16-byte aligned.  Asynchronous. */
 int32_t bwtk_download(const void *d_src, void *h_pinned, int64_t bytes, void *stream);
 
+/* ---- device memory for hosts without a CUDA allocator of their own ---------------------------------
+ * The entry points of this header take raw device pointers from any allocator (torch, cudaMalloc, a pool).
+ * A host that has none -- the drop-in CLI answering `python bwt.py small.fa` (bwt.py:4201-4370) before an
+ * `import torch` would have finished, or a C caller -- gets buffers here.  bwtk_device_count: visible CUDA
+ * devices (0 without a driver; never an error).  bwtk_dev_alloc / bwtk_dev_free: cudaMalloc / cudaFree on the
+ * current device (256-byte aligned).  bwtk_copy_to_device / bwtk_copy_to_host: pageable or pinned host memory,
+ * on `stream`, synchronous (they return when the bytes have arrived). */
+int32_t bwtk_device_count(int32_t *count);
+int32_t bwtk_dev_alloc(void **d_ptr, int64_t bytes);
+int32_t bwtk_dev_free(void *d_ptr);
+int32_t bwtk_copy_to_device(void *d_dst, const void *h_src, int64_t bytes, void *stream);
+int32_t bwtk_copy_to_host(void *h_dst, const void *d_src, int64_t bytes, void *stream);
+
 /* ---- FASTA ingest: TandemRepeatFinder.load_reference (bwt.py:3713-3756), host code -----
  * Two passes over the file's bytes with the reference's line rules (strip, '>' headers, first
  * token = name, upper-case, lines before the first header dropped; line ends \n, \r\n, \r).

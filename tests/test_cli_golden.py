@@ -164,3 +164,42 @@ def test_cli_synC_bed_md5_on_gpu(tmp_path, capsys, jobs):
     data = out.read_bytes()
     assert data.count(b"\n") == 565
     assert hashlib.md5(data).hexdigest() == SYNC_BED_MD5
+
+
+@pytest.mark.gpu
+def test_cli_fresh_process_answers_without_importing_torch(tmp_path):
+    """`python bwt.py ...` in a fresh interpreter: the detector call runs on the library's own buffers (lean.py) and
+    torch is never imported -- same bytes as the reference CLI for synC (md5) and for a multi-contig fixture in two
+    formats, with --jobs 4 (chain pool) and --jobs -1; with BWTK_LEAN=0 the same process goes through torch."""
+    import hashlib
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fa = tmp_path / "synC.fa"
+    _write_sync(fa)
+    prog = ("import sys; sys.path.insert(0, {root!r}); import bwt; bwt.main({argv!r}); "
+            "print('TORCH_IMPORTED', 'torch' in sys.modules)")
+
+    def run(argv, **env):
+        res = subprocess.run([sys.executable, "-c", prog.format(root=root, argv=argv)], capture_output=True, text=True,
+                             env=dict(os.environ, **env), timeout=300)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        assert "ERROR" not in res.stdout, res.stdout[-2000:]
+        return res.stdout
+
+    for jobs in ("0", "-1"):
+        out = tmp_path / f"synC_{jobs}.bed"
+        stdout = run([str(fa), "-o", str(out), "--jobs", jobs, "--format", "bed"])
+        assert "TORCH_IMPORTED False" in stdout
+        assert hashlib.md5(out.read_bytes()).hexdigest() == SYNC_BED_MD5
+    fixture, flags, tag = next(c for c in CASES if c[0] == "test2.fa" and not c[1])
+    for fmt in ("bed", "strfinder"):
+        out = tmp_path / f"{tag}.{fmt}"
+        stdout = run([os.path.join(CLI, fixture), "-o", str(out), "--format", fmt, "--jobs", "4"] + flags)
+        assert "TORCH_IMPORTED False" in stdout
+        assert out.read_text() == _expected(tag, fmt)
+    out = tmp_path / "synC_torch.bed"
+    stdout = run([str(fa), "-o", str(out), "--jobs", "0", "--format", "bed"], BWTK_LEAN="0")
+    assert "TORCH_IMPORTED True" in stdout
+    assert hashlib.md5(out.read_bytes()).hexdigest() == SYNC_BED_MD5
