@@ -130,10 +130,11 @@ def _contig_finder(chrom: str, seq: str, config: dict, left: str, right: str) ->
     return finder
 
 
-def _process_and_finish_contig(args):
+def _process_and_finish_contig(args, pool=None):
     """Worker of the per-contig path: detection (bwt.py:3040-3141) at row level, then this contig's share of
     the post-processing chain on the rows (rowchain.finish_rows) -- records are only built for the calls
-    that survive.  Returns (final calls, raw, after suppression, after dedup)."""
+    that survive.  Returns (final calls, raw, after suppression, after dedup).  `pool`: CPU worker processes
+    that finish independent pieces of the contig's rows side by side (_run_with_segment_pool)."""
     chrom, seq, config, left, right = args
     try:
         rows, text_arr = _detect_rows(chrom, seq, config)
@@ -146,14 +147,15 @@ def _process_and_finish_contig(args):
     n_raw = 0 if rows is None else len(rows)
     if not n_raw:
         return [], 0, 0, 0
-    return _finish_contig_rows((chrom, seq, config, left, right, rows, text_arr))
+    return _finish_contig_rows((chrom, seq, config, left, right, rows, text_arr), pool)
 
 
-def _finish_contig_rows(args):
+def _finish_contig_rows(args, pool=None):
     """The host half of the per-contig path: this contig's share of the post-processing chain on the detector's
     rows.  CPU only (NumPy + the host functions of libbwtk.so), so it can run in a pool of plain worker processes
     while the parent keeps the GPU busy with the next contig.  `seq` may be None for an ASCII contig: it is the
-    text without its sentinel."""
+    text without its sentinel.  With a `pool` and enough rows the contig is cut into independent pieces
+    (rowchain.finish_rows_segmented) that the pool's workers finish side by side."""
     chrom, seq, config, left, right, rows, text_arr = args
     n_raw = len(rows)
     try:
@@ -161,13 +163,90 @@ def _finish_contig_rows(args):
 
         if seq is None:
             seq = text_arr[:-1].tobytes().decode("ascii")
-        return rowchain.finish_rows(_contig_finder(chrom, seq, config, left, right), chrom, text_arr, rows)
+        finder = _contig_finder(chrom, seq, config, left, right)
+        if pool is not None and n_raw >= 2 * rowchain.SEGMENT_MIN_ROWS:
+            try:
+                return _finish_rows_in_pool(pool, finder, chrom, seq, config, left, right, rows, text_arr)
+            except Exception as exc:  # a lost worker must not lose the contig: finish it here
+                print(f"WARNING: chain workers failed for {chrom} ({exc}); finishing in-process")
+        return rowchain.finish_rows(finder, chrom, text_arr, rows)
     except Exception as exc:  # same policy as the detection worker
         print(f"ERROR post-processing chromosome {chrom}: {exc}")
         import traceback
 
         traceback.print_exc()
         return [], n_raw, n_raw, n_raw
+
+
+def _finish_rows_in_pool(pool, finder, chrom, seq, config, left, right, rows, text_arr):
+    """One contig's rows, cut into independent pieces, finished by the workers of `pool`.  The text goes to the
+    workers once, through a file in a temporary directory (they read it on their first piece); the pieces' rows and
+    the finished calls travel through the pool's pipes."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+
+    from . import rowchain
+
+    tmp = tempfile.mkdtemp(prefix="bwtk_chain_")
+    try:
+        path = os.path.join(tmp, "text.u8")
+        np.ascontiguousarray(text_arr, np.uint8).tofile(path)
+        head = (chrom, None if seq.isascii() else seq, config, left, right, path)
+
+        def run_pieces(parts):
+            jobs = [pool.apply_async(_finish_piece, (head + (np.ascontiguousarray(p[:, :4]),),)) for p in parts]
+            return [j.get() for j in jobs]
+
+        return rowchain.finish_rows_segmented(finder, chrom, text_arr, rows, run_pieces,
+                                              pieces=max(1, getattr(pool, "_processes", 1)))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+_PIECE_TEXT: Dict[str, tuple] = {}      # worker side: text file -> (text_arr, finder) of the contig in progress
+
+
+def _finish_piece(args):
+    """Pool worker of _finish_rows_in_pool: one piece of one contig's rows -> rowchain.finish_segment."""
+    import numpy as np
+
+    from . import rowchain
+
+    chrom, seq, config, left, right, path, rows = args
+    got = _PIECE_TEXT.get(path)
+    if got is None:
+        _PIECE_TEXT.clear()
+        text_arr = np.fromfile(path, np.uint8)
+        if seq is None:
+            seq = text_arr[:-1].tobytes().decode("ascii")
+        got = _PIECE_TEXT[path] = (text_arr, _contig_finder(chrom, seq, config, left, right))
+    text_arr, finder = got
+    return rowchain.finish_segment(finder, chrom, text_arr, rows)
+
+
+# One large contig on one GPU: its chain is cut into pieces for this many CPU workers (--jobs) from this many
+# bases on; below it the chain is faster than starting the workers.  Tests lower it.
+SEGMENT_POOL_MIN_BASES = 8_000_000
+
+
+def _segment_pool_size(tasks: List[Tuple], n_jobs: int) -> int:
+    if not tasks or (n_jobs or 1) < 2 or max(len(t[1]) for t in tasks) < SEGMENT_POOL_MIN_BASES:
+        return 0
+    return max(2, min(int(n_jobs), cpu_count()))
+
+
+def _run_with_segment_pool(tasks: List[Tuple], procs: int):
+    """Per-contig path for a few large contigs on ONE GPU: contig after contig, detection here, the chain of every
+    contig cut into independent pieces for `procs` spawned CPU workers.  The workers start (interpreter, NumPy,
+    this package) while the first contig is on the GPU."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")          # never fork a process that holds a CUDA context
+    with ctx.Pool(procs) as pool:
+        for task in tasks:
+            yield _process_and_finish_contig(task, pool=pool)
 
 
 # The chain pool (one GPU, several contigs): from this many bases on, the contigs' chains go to CPU worker
@@ -500,9 +579,17 @@ class TandemRepeatFinder:
             finished: List[TandemRepeat] = []
             n_raw = n_kept = n_unique = 0
             ftasks = self._finish_tasks(tasks)
-            pool_procs = 0 if sharding.worker_processes(len(ftasks), n_jobs) > 1 else _chain_pool_size(ftasks, n_jobs)
-            results = (_run_with_chain_pool(ftasks, pool_procs) if pool_procs
-                       else sharding.run_tasks(_process_and_finish_contig, ftasks, n_jobs))
+            # one process per GPU when there are several; on one GPU the host side is spread over CPU workers:
+            # whole contigs when there are at least as many as workers, pieces of a contig's chain otherwise
+            one_gpu = sharding.worker_processes(len(ftasks), n_jobs) <= 1
+            pool_procs = _chain_pool_size(ftasks, n_jobs) if one_gpu else 0
+            seg_procs = _segment_pool_size(ftasks, n_jobs) if one_gpu else 0
+            if seg_procs and (not pool_procs or len(ftasks) < seg_procs):
+                results = _run_with_segment_pool(ftasks, seg_procs)
+            elif pool_procs:
+                results = _run_with_chain_pool(ftasks, pool_procs)
+            else:
+                results = sharding.run_tasks(_process_and_finish_contig, ftasks, n_jobs)
             for part, a, b, c in results:
                 finished.extend(part)
                 n_raw, n_kept, n_unique = n_raw + a, n_kept + b, n_unique + c

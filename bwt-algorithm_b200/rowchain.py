@@ -24,7 +24,7 @@ concatenates contigs and sorts (every stage of the chain acts inside one contig)
 from __future__ import annotations
 
 import copy
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 
@@ -69,12 +69,17 @@ def suppress_rows(rows: np.ndarray, overlap_threshold: float = 0.5) -> np.ndarra
     return keep.astype(bool)
 
 
-def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> Tuple[List[TandemRepeat], int, int, int]:
+def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray,
+                info: Optional[dict] = None) -> Tuple[List[TandemRepeat], int, int, int]:
     """The whole chain for the exact (mismatch-free) strict-scan rows of one contig.
 
     `finder` is a ``TandemRepeatFinder`` that knows this contig (sequences / full_sequences /
     trim_offsets); returns (final calls, raw, after suppression, after dedup) like
-    ``TandemRepeatFinder._postprocess_counts``."""
+    ``TandemRepeatFinder._postprocess_counts``.  `info` (optional) receives ``reach``: the first position at which a
+    later call could no longer be merged into, or collapse with, anything this chain formed beyond its rows (merged
+    and re-aligned calls: end + motif length + 1) -- what ``finish_rows_segmented`` checks its cuts against."""
+    if info is not None:
+        info["reach"] = -1
     n_raw = int(rows.shape[0])
     if n_raw == 0:
         return [], 0, 0, 0
@@ -103,11 +108,16 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
     m = int(idx.size)
     Cn = rows[idx, 3].astype(np.int64)
 
-    text_bytes = text_arr.tobytes()
+    # the contig's bytes, kept on the finder while it is finishing pieces of the same text
+    held = finder.__dict__.get("_chain_text")
+    if held is None or held[0] is not text_arr:
+        held = finder.__dict__["_chain_text"] = (text_arr, text_arr.tobytes())
+    text_bytes = held[1]
     maker = StrictRecordMaker(text_arr, chrom, 0, text_bytes)
-    # the contig as the chain's re-alignments see it (finder.sequences: no sentinel)
+    # the contig as the chain's re-alignments see it (finder.sequences: no sentinel); every slice below ends at or
+    # before seq_len, so the text's own bytes serve
     seq_len = len(finder.sequences.get(chrom) or "")
-    seq_bytes = text_bytes[:seq_len]
+    seq_bytes = text_bytes
     fast_k1 = FAST_K1 and seq_len > 0 and min_copies >= 1
 
     def make_row(i: int) -> TandemRepeat:
@@ -153,14 +163,17 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
         next_l[:-1] = link[1:]
         iso = np.flatnonzero(link & (K == 1) & ~prev_l & ~next_l)
         if iso.size:
-            seq_arr = text_arr[:seq_len]
-            bounds = np.flatnonzero(seq_arr[1:] != seq_arr[:-1]) + 1      # starts of the maximal runs
             s0 = S[iso]
             e_max = np.maximum(E[iso], E[iso + 1])
             stop = np.minimum(seq_len, np.maximum(e_max, s0 + max(1, min_copies)) + 4)
+            # starts of the maximal runs, inside the window these events can see (a piece of a contig only looks at
+            # its own stretch); a run that leaves the window ends beyond every stop, which caps it
+            w0, w1 = int(s0.min()), min(seq_len, int(stop.max()) + 1)
+            window = text_arr[w0:w1]
+            bounds = np.flatnonzero(window[1:] != window[:-1]) + 1 + w0
             bi = np.searchsorted(bounds, s0, side="right")
-            run_end = np.where(bi < bounds.size, bounds[np.minimum(bi, max(bounds.size - 1, 0))], seq_len) \
-                if bounds.size else np.full(iso.size, seq_len, np.int64)
+            run_end = np.where(bi < bounds.size, bounds[np.minimum(bi, max(bounds.size - 1, 0))], w1) \
+                if bounds.size else np.full(iso.size, w1, np.int64)
             run = np.minimum(run_end, stop) - s0
             nxt = iso + 2
             has = nxt < m
@@ -276,6 +289,16 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
             r = finder._recompute_repeat(r.chrom, r.start, r.end, k, tier_hint=r.tier)
         rec_list.append(r)
         rec_slot.append(slot)
+    if info is not None:
+        reach = -1
+        for _, r in merged:                               # as merged (before the refinement moved their ends)
+            reach = max(reach, r.end + len(r.consensus_motif or r.motif) + 1)
+        for r in rec_list:
+            reach = max(reach, r.end + len(r.consensus_motif or r.motif) + 1)
+        virt_i = np.flatnonzero(alive & (vrun > 0))
+        if virt_i.size:
+            reach = max(reach, int((S[virt_i] + vrun[virt_i]).max()) + 2)
+        info["reach"] = reach
     rpos = np.flatnonzero(alive)                          # rows and virtual items, by list slot
     n_rows_items = int(rpos.size)
     ref = np.concatenate((rpos, -1 - np.arange(len(rec_list), dtype=np.int64)))     # >= 0: position i; < 0: record
@@ -413,6 +436,75 @@ def finish_rows(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray) -> T
     q_all = np.concatenate((plain, o_keys[:, 2]))
     every = made + [r for _, r in out]
     return [every[i] for i in np.lexsort((q_all, e_all, s_all)).tolist()], n_raw, n_kept, n_unique
+
+
+# ---- one contig, several processes -------------------------------------------------------------------
+# Every stage of the chain is local: a call interacts with another only by overlapping it (suppression, collapse)
+# or by starting within motif length + 1 of its end (merge), and what a merge forms extends forwards only.  So
+# the rows, sorted by start, can be cut wherever every row before the cut ends more than its motif length + 1
+# before the next row starts; the pieces are finished independently (in worker processes) and concatenated.  The
+# one thing a cut cannot know beforehand is how far a merged, re-aligned call reaches beyond its rows: every piece
+# reports that (``info["reach"]``), and if any piece reached the first row of the next one the contig is finished
+# in one piece instead.
+SEGMENT_MIN_ROWS = 200_000        # below this the chain is faster than starting workers; tests lower it
+
+
+def segment_bounds(rows: np.ndarray, order: np.ndarray, pieces: int, min_rows: int) -> List[int]:
+    """Boundaries (indices into `order`, the rows' stable order by start) of at most `pieces` independent
+    pieces of at least `min_rows` rows: [0, ..., len(rows)]."""
+    n = int(order.size)
+    if pieces < 2 or n < 2 * max(1, min_rows):
+        return [0, n]
+    S = rows[order, 0].astype(np.int64)
+    reach = np.maximum.accumulate(rows[order, 1].astype(np.int64) + rows[order, 2].astype(np.int64) + 1)
+    room = S[1:] - reach[:-1]                                # > 0: a piece may start at row i + 1
+    pieces = min(pieces, max(1, n // max(1, min_rows)))
+    look = max(1, min(4096, min_rows // 4))                  # rows around the even split among which a cut is chosen
+    bounds = [0]
+    for t in range(1, pieces):
+        want = n * t // pieces
+        lo, hi = max(1, want - look), min(n - 1, want + look)
+        if lo >= hi:
+            continue
+        # the widest gap nearby: what a merge forms beyond its rows (the re-alignment walks a few motif lengths
+        # past them) must stay clear of the next piece's first row, or the contig is finished in one piece
+        at = int(np.argmax(room[lo - 1:hi - 1])) + lo
+        if room[at - 1] > 0 and at - bounds[-1] >= min_rows and n - at >= min_rows:
+            bounds.append(at)
+    bounds.append(n)
+    return bounds
+
+
+def finish_segment(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray):
+    """One piece: (final calls, raw, kept, unique, reach)."""
+    info: dict = {}
+    final, a, b, c = finish_rows(finder, chrom, text_arr, rows, info)
+    return final, a, b, c, info["reach"]
+
+
+def finish_rows_segmented(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray, run_pieces, pieces: int,
+                          min_rows: Optional[int] = None) -> Tuple[List[TandemRepeat], int, int, int]:
+    """``finish_rows`` with the contig's rows cut into independent pieces.  `run_pieces(list of row arrays)` returns
+    ``finish_segment``'s result for every piece, in order (the caller decides where they run: a process pool
+    in the CLI, a plain loop in the tests).  Same calls, same order, same counts as ``finish_rows``."""
+    rows = np.ascontiguousarray(rows, np.int32)
+    order = np.argsort(rows[:, 0], kind="stable")
+    bounds = segment_bounds(rows, order, pieces, SEGMENT_MIN_ROWS if min_rows is None else min_rows)
+    if len(bounds) <= 2:
+        return finish_rows(finder, chrom, text_arr, rows)
+    # a piece keeps the arrival order of its rows (the chain's tie rules look at it)
+    parts = [rows[np.sort(order[bounds[i]:bounds[i + 1]])] for i in range(len(bounds) - 1)]
+    firsts = [int(rows[order[b], 0]) for b in bounds[1:-1]]
+    results = run_pieces(parts)
+    for (_, _, _, _, reach), first in zip(results[:-1], firsts):
+        if reach >= first:                       # a merged call of this piece could have met the next piece's rows
+            return finish_rows(finder, chrom, text_arr, rows)
+    final: List[TandemRepeat] = []
+    n_raw = n_kept = n_unique = 0
+    for part, a, b, c, _ in results:
+        final.extend(part)
+        n_raw, n_kept, n_unique = n_raw + a, n_kept + b, n_unique + c
+    return final, n_raw, n_kept, n_unique
 
 
 def _finish_rows_slow(finder, chrom: str, text_arr: np.ndarray, rows: np.ndarray):

@@ -167,6 +167,29 @@ def test_cli_synC_bed_md5_on_gpu(tmp_path, capsys, jobs):
 
 
 @pytest.mark.gpu
+def test_cli_segment_pool_on_gpu(tmp_path, capsys, monkeypatch):
+    """One contig, --jobs 4: detection in this process, the contig's chain cut into pieces for spawned CPU workers
+    (pipeline._run_with_segment_pool, forced on for the 150 kb contig).  The reference CLI's bytes, by md5."""
+    import hashlib
+
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200 import bwt, pipeline, rowchain, sharding
+
+    fa, out = tmp_path / "synC.fa", tmp_path / "synC.bed"
+    _write_sync(fa)
+    monkeypatch.setattr(pipeline, "SEGMENT_POOL_MIN_BASES", 0)
+    monkeypatch.setattr(rowchain, "SEGMENT_MIN_ROWS", 500)
+    monkeypatch.setattr(sharding, "worker_processes", lambda n_tasks, n_jobs: 1)
+    used = []
+    real = pipeline._finish_rows_in_pool
+    monkeypatch.setattr(pipeline, "_finish_rows_in_pool", lambda *a, **k: used.append(1) or real(*a, **k))
+    bwt.main([str(fa), "-o", str(out), "--jobs", "4", "--format", "bed"])
+    capsys.readouterr()
+    assert used
+    assert hashlib.md5(out.read_bytes()).hexdigest() == SYNC_BED_MD5
+
+
+@pytest.mark.gpu
 def test_cli_fresh_process_answers_without_importing_torch(tmp_path):
     """`python bwt.py ...` in a fresh interpreter: the detector call runs on the library's own buffers (lean.py) and
     torch is never imported -- same bytes as the reference CLI for synC (md5) and for a multi-contig fixture in two

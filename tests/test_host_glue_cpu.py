@@ -563,3 +563,120 @@ def test_row_chain_requeues_an_undone_homopolymer_event():
         assert fast[1:] == slow[1:]
         assert [dataclasses.astuple(r) for r in fast[0]] == [dataclasses.astuple(r) for r in slow[0]]
     assert hits >= 3
+
+
+def _strict_rows_numpy(s: np.ndarray, max_unit: int, min_copies: int = 3) -> np.ndarray:
+    """Strict-scan rows (bwt.py:1891-2001 semantics for max_mismatch 0) by run lengths in NumPy -- fast enough for
+    long texts with small unit caps (the oracle's loop is quadratic in the unit length).  Checked against the oracle
+    in test_segmented_chain_equals_the_whole_chain."""
+    out = []
+    n = s.size
+    for u in range(min(max_unit, n // min_copies), 0, -1):
+        eq = s[:-u] == s[u:]
+        d = np.diff(np.concatenate([[0], eq.view(np.int8), [0]]))
+        a, b = np.flatnonzero(d == 1), np.flatnonzero(d == -1)
+        keep = (b - a) >= (min_copies - 1) * u
+        prev_end = -1
+        for x, y in zip(a[keep].tolist(), b[keep].tolist()):
+            e = x if x > prev_end else prev_end
+            if e <= y - (min_copies - 1) * u:
+                cnt = 1 + (y - e) // u
+                prev_end = e + cnt * u
+                unit = s[e:e + u].tobytes()
+                prim = next((p for p in range(1, u // 2 + 1) if u % p == 0 and unit[p:] == unit[:-p]), u)
+                out.append((e, prev_end, prim, (prev_end - e) // prim if prim < u else cnt, 0, 0, u, 0))
+    return np.array(out, np.int32).reshape(-1, 8)
+
+
+def test_segmented_chain_equals_the_whole_chain(oracle):
+    """rowchain.finish_rows_segmented cuts a contig's rows where no row reaches the next one, finishes the pieces
+    independently and checks afterwards that nothing a piece formed reached its neighbour.  Same calls, order and
+    counts as finish_rows -- with pieces of a handful of rows, so that cuts fall next to merge chains, nested calls,
+    collapsing calls and contig ends all the time (and the one-piece fallback is exercised too)."""
+    import dataclasses
+
+    from bwt_algorithm_b200 import pipeline, rowchain
+    from tests.util import gen_contig
+
+    cfg = {"sa_sample_rate": 32, "show_progress": False, "allow_mismatches": True, "max_motif_length": 9,
+           "min_period": 10, "max_period": 1000, "min_copies": 3, "min_entropy": 1.0, "max_unit_len": 120}
+    rng = np.random.default_rng(19)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    planted = gen_contig(60_000, 5)
+    dense = gen_contig(30_000, 6, sub_rate=0.08)
+    lowc = np.frombuffer(b"AATTAC", np.uint8)[rng.integers(0, 6, 40_000)]
+    two = np.frombuffer(b"AT", np.uint8)[rng.integers(0, 2, 20_000)]
+    drift = np.tile(np.frombuffer(b"AACAACAAGAAG", np.uint8), 1500)            # one long chain of merges (unit 3)
+    drift[rng.integers(0, drift.size, 150)] = acgt[rng.integers(0, 4, 150)]
+    texts = {"planted": (planted, 40), "dense": (dense, 40), "low_complexity": (lowc, 12), "two_letters": (two, 12),
+             "drift": (drift, 24), "drift_short_units": (drift, 9)}
+    assert np.array_equal(_strict_rows_numpy(planted[:6000], 40), oracle.strict_scan(planted[:6000].tobytes() + b"$", 1, 40, 0, 3))
+    fallbacks = pieces_run = 0
+    for name, (s, cap) in texts.items():
+        rows = _strict_rows_numpy(s, cap)
+        seq = s.tobytes().decode()
+        text = np.frombuffer((seq + "$").encode(), np.uint8)
+        whole = rowchain.finish_rows(pipeline._contig_finder("c1", seq, cfg, "", ""), "c1", text, rows)
+        want = [dataclasses.astuple(r) for r in whole[0]]
+        assert len(want) > 10, name
+        for min_rows, pieces in ((3, 1000), (25, 64), (400, 7)):
+            finder = pipeline._contig_finder("c1", seq, cfg, "", "")
+            ran = []
+
+            def run_pieces(parts, finder=finder, ran=ran):
+                ran.append(len(parts))
+                return [rowchain.finish_segment(finder, "c1", text, p) for p in parts]
+
+            got = rowchain.finish_rows_segmented(finder, "c1", text, rows, run_pieces, pieces, min_rows)
+            assert got[1:] == whole[1:], (name, min_rows)
+            assert [dataclasses.astuple(r) for r in got[0]] == want, (name, min_rows)
+            pieces_run += sum(ran)
+            # the fallback is visible as a reach beyond a neighbour's first row; count it through a dry run
+            order = np.argsort(rows[:, 0], kind="stable")
+            bounds = rowchain.segment_bounds(rows, order, pieces, min_rows)
+            if len(bounds) > 2:
+                parts = [rows[np.sort(order[bounds[i]:bounds[i + 1]])] for i in range(len(bounds) - 1)]
+                firsts = [int(rows[order[b], 0]) for b in bounds[1:-1]]
+                reaches = [rowchain.finish_segment(finder, "c1", text, p)[4] for p in parts[:-1]]
+                fallbacks += any(r >= f for r, f in zip(reaches, firsts))
+    assert pieces_run > 500 and fallbacks >= 1
+
+
+def test_segment_pool_finishes_one_contig_in_pieces(oracle, monkeypatch, capsys, tmp_path):
+    """One large contig on one GPU with --jobs > 1: the contig's chain is cut into pieces for spawned CPU workers
+    (pipeline._run_with_segment_pool -> _finish_rows_in_pool -> _finish_piece).  Same calls and summary lines as the
+    in-process chain; the text reaches the workers through a temporary file that is gone afterwards."""
+    import dataclasses
+    import glob
+    import os
+    import tempfile
+
+    from bwt_algorithm_b200 import pipeline, rowchain, sharding
+    from tests.util import gen_contig
+
+    s = gen_contig(90_000, 31)
+    fa = tmp_path / "one.fa"
+    fa.write_text(">big one contig\n" + s.tobytes().decode() + "\n")
+
+    def fake_rows(chrom, seq, config):
+        text = np.frombuffer((seq + "$").encode(), np.uint8)
+        return _strict_rows_numpy(text[:-1], 60, config["min_copies"]), text
+
+    monkeypatch.setattr(pipeline, "_detect_rows", fake_rows)
+    monkeypatch.setattr(sharding, "worker_processes", lambda n_tasks, n_jobs: 1)
+    outs = []
+    for min_bases, min_rows, jobs in ((1 << 40, 1 << 40, 3), (0, 200, 3)):
+        monkeypatch.setattr(pipeline, "SEGMENT_POOL_MIN_BASES", min_bases)
+        monkeypatch.setattr(rowchain, "SEGMENT_MIN_ROWS", min_rows)
+        used = []
+        real = pipeline._finish_rows_in_pool
+        monkeypatch.setattr(pipeline, "_finish_rows_in_pool", lambda *a, **k: used.append(1) or real(*a, **k))
+        finder = TandemRepeatFinder(str(fa))
+        finder.load_reference()
+        final = finder.find_tandem_repeats_parallel(enable_tier1=False, enable_tier2=True, n_jobs=jobs)
+        lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith(("Nested call", "Analysis complete"))]
+        outs.append(([dataclasses.astuple(r) for r in final], lines))
+        assert bool(used) == (min_bases == 0)
+        monkeypatch.setattr(pipeline, "_finish_rows_in_pool", real)
+    assert len(outs[0][0]) > 100 and outs[0] == outs[1]
+    assert not glob.glob(os.path.join(tempfile.gettempdir(), "bwtk_chain_*"))
