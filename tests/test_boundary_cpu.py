@@ -49,6 +49,36 @@ def test_product_has_no_cpu_fallback():
         IndexPipeline(1000)
 
 
+def test_start_up_path_without_torch_needs_a_gpu_too():
+    """lean.py (the CLI's detector call on the library's own buffers while torch is not loaded) is a start-up path,
+    not a fallback: without a device it reports zero devices and the worker goes on to the torch path, which raises;
+    its own calls fail loudly; and it steps aside as soon as torch is in the process or BWTK_LEAN=0."""
+    import subprocess
+    import sys
+
+    import torch
+
+    import bwt_algorithm_b200  # noqa: F401
+    from bwt_algorithm_b200 import _lib, lean, pipeline
+
+    assert "torch" in sys.modules and not lean.enabled()
+    probe = ("import sys; sys.path.insert(0, %r); import bwt_algorithm_b200; from bwt_algorithm_b200 import lean; "
+             "print(lean.enabled(), lean.device_count(), 'torch' in sys.modules)" % ROOT)
+    out = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "True" and out[2] == "False"
+    off = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, check=True,
+                         env=dict(os.environ, BWTK_LEAN="0")).stdout.split()
+    assert off[0] == "False"
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert out[1] == "0" and lean.device_count() == 0
+    with pytest.raises(_lib.BwtkError):
+        lean.strict_rows(np.frombuffer(b"ACACACACAC$", np.uint8), 1, 4, 0, 3)
+    with pytest.raises(_lib.BwtkError):
+        pipeline._detect_rows("c", "ACACACACACAC", {"sa_sample_rate": 32, "enable_tier2": True, "min_copies": 3,
+                                                    "max_unit_len": 120})
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "bwt-algorithm_b200")
     for dirpath, _dirs, files in os.walk(pkg):
