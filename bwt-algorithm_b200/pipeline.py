@@ -234,7 +234,7 @@ SEGMENT_POOL_MIN_BASES = 8_000_000
 def _segment_pool_size(tasks: List[Tuple], n_jobs: int) -> int:
     if not tasks or (n_jobs or 1) < 2 or max(len(t[1]) for t in tasks) < SEGMENT_POOL_MIN_BASES:
         return 0
-    return max(2, min(int(n_jobs), cpu_count()))
+    return max(2, min(int(n_jobs), cpu_count(), 16))      # beyond that the parent (unpickling the calls) is the limit
 
 
 def _run_with_segment_pool(tasks: List[Tuple], procs: int):
@@ -558,6 +558,7 @@ class TandemRepeatFinder:
         because everything is re-sorted afterwards."""
         from . import sharding
 
+        host_jobs = cpu_count() if n_jobs is None else n_jobs      # CPU workers for the host chain: --jobs 0 = all cores
         if n_jobs is None:
             n_jobs = min(cpu_count(), len(self.sequences))
         print(f"Parallel mode: Using {n_jobs} CPU cores for {len(self.sequences)} chromosomes")
@@ -582,8 +583,8 @@ class TandemRepeatFinder:
             # one process per GPU when there are several; on one GPU the host side is spread over CPU workers:
             # whole contigs when there are at least as many as workers, pieces of a contig's chain otherwise
             one_gpu = sharding.worker_processes(len(ftasks), n_jobs) <= 1
-            pool_procs = _chain_pool_size(ftasks, n_jobs) if one_gpu else 0
-            seg_procs = _segment_pool_size(ftasks, n_jobs) if one_gpu else 0
+            pool_procs = _chain_pool_size(ftasks, host_jobs) if one_gpu else 0
+            seg_procs = _segment_pool_size(ftasks, host_jobs) if one_gpu else 0
             if seg_procs and (not pool_procs or len(ftasks) < seg_procs):
                 results = _run_with_segment_pool(ftasks, seg_procs)
             elif pool_procs:
