@@ -13,7 +13,7 @@ Layout in HBM (all torch tensors on one CUDA device):
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Sequence, Tuple
 
 import numpy as np
 

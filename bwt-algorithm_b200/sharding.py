@@ -8,8 +8,7 @@ own GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
-import os
-from typing import Callable, Iterable, Iterator, List, Sequence, Tuple
+from typing import Callable, Iterator, List, Sequence, Tuple
 
 import numpy as np
 
