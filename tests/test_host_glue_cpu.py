@@ -337,6 +337,23 @@ def test_postprocessing_chain_equals_reference_golden():
     rfinal, n_raw, n_kept, n_unique = rowchain.finish_rows(f, g["chrom"], np.frombuffer(seq.encode(), np.uint8), rows)
     assert [n_raw, n_kept, n_unique] == g["stage_counts"][:3]
     assert digest(rfinal) == g["digest"] and [r.to_bed() for r in rfinal] == g["bed"]
+    # ... also when the contig's rows are cut into independent pieces (what the CLI's CPU workers are handed) ...
+    text = np.frombuffer(seq.encode(), np.uint8)
+    for pieces, min_rows in ((4, 300), (40, 20), (1000, 3)):
+        ran = []
+
+        def run_pieces(parts, ran=ran):
+            ran.append(len(parts))
+            return [rowchain.finish_segment(f, g["chrom"], text, p) for p in parts]
+
+        sfinal, a, b, c = rowchain.finish_rows_segmented(f, g["chrom"], text, rows, run_pieces, pieces, min_rows)
+        assert [a, b, c] == g["stage_counts"][:3] and ran and ran[0] > 1
+        assert digest(sfinal) == g["digest"]
+    # ... and with the re-alignment walk in Python instead of native code (the default above)
+    slow = TandemRepeatFinder("/dev/null")
+    slow._NATIVE_WALK = False
+    slow.sequences, slow.full_sequences, slow.trim_offsets = f.sequences, f.full_sequences, f.trim_offsets
+    assert digest(rowchain.finish_rows(slow, g["chrom"], text, rows)[0]) == g["digest"]
 
 
 def test_per_contig_finish_equals_global_chain(oracle, tmp_path):
