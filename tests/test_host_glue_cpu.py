@@ -196,6 +196,31 @@ def test_native_walk_equals_python_walk():
     assert cases > 5000 and summaries > 1500 and min(with_sub, with_ins, with_del) > 40
 
 
+def test_both_walks_equal_the_reference_on_its_own_answers():
+    """tests/golden/align_walk.json (oracle/gen_align_golden.py): the UNMODIFIED reference's
+    MotifUtils.align_repeat_region on 2 400 seeded cases.  The Python port and the native walk give the same
+    consensus, copy count, consumed span, mismatch rate, worst copy, variation notes and indel totals (or None)."""
+    import json
+    import os
+
+    from bwt_algorithm_b200.motifs import align_region_native
+    from tests.align_cases import cases
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "align_walk.json")) as fh:
+        g = json.load(fh)
+    n = notes = 0
+    for (seq, start, end, template, frac, max_indel, min_copies), want in zip(cases(), g["answers"]):
+        want = None if want is None else tuple(want)
+        port = _walk_fields(MotifUtils.align_repeat_region(seq, start, end, template, frac, max_indel, min_copies))
+        assert port == want, (seq, start, end, template, frac, max_indel, min_copies)
+        native = align_region_native(seq.encode("ascii"), start, end, template.encode("ascii"), frac, max_indel,
+                                     min_copies)
+        assert native is not NotImplemented and native == want, (seq, start, end, template, frac, max_indel, min_copies)
+        n += 1
+        notes += bool(want and want[5])
+    assert n == g["cases"] == 2400 and notes > 300
+
+
 def test_native_walk_declines_what_it_cannot_represent():
     """More than eight distinct symbols in one consensus column: the native walk says NotImplemented and
     _recompute_repeat takes the Python walk -- same record either way; a non-ASCII contig never reaches it."""
