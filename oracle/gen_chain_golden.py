@@ -20,6 +20,8 @@ sys.dont_write_bytecode = True
 REF_DIR = os.environ.get("BWT_REFERENCE_DIR", "/root/reference")
 
 N, SEED, FLANK = 60_000, 33, 30
+# (file, generator, n, seed): the Appendix B contig, and an indel-rich one with arrays close together
+FIXTURES = [("chain_60k.json", "gen_contig", 60_000, 33), ("chain_indel_30k.json", "gen_contig_indel", 30_000, 7)]
 
 
 def digest(records) -> str:
@@ -27,18 +29,24 @@ def digest(records) -> str:
 
 
 def main():
+    for name, gen, n, seed in FIXTURES:
+        if len(sys.argv) < 2 or sys.argv[1] == name:
+            one(name, gen, n, seed)
+
+
+def one(name, gen, N, SEED):
     import numpy as np
 
     import bwt_algorithm_b200  # noqa: F401
     from bwt_algorithm_b200 import finders
     from oracle import oracle as orc
-    from tests.util import gen_contig
+    from tests import util
 
     spec = importlib.util.spec_from_file_location("refbwt", os.path.join(REF_DIR, "bwt.py"))
     ref = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref)
 
-    arr = gen_contig(N, SEED)
+    arr = getattr(util, gen)(N, SEED)
     full = arr.tobytes().decode()
     seq = full[FLANK:len(full) - FLANK]                      # what load_reference hands to the worker
     trimmed = np.frombuffer(seq.encode(), np.uint8)
@@ -54,16 +62,17 @@ def main():
     refined = f._collapse_overlapping_repeats(refined)
     final = [r for r in refined if r.copies >= f.min_copies and r.length >= 6]
     final.sort(key=f._repeat_sort_key)
-    out = {"n": N, "seed": SEED, "flank": FLANK, "chrom": "synC",
+    out = {"n": N, "seed": SEED, "flank": FLANK, "chrom": "synC", "generator": gen,
            "rows": rows[:, :4].tolist(),
            "stage_counts": [len(raw), len(kept), len(unique), len(merged), len(refined), len(final)],
            "digest": digest(final), "digest_before_filter": digest(refined),
            "bed": [r.to_bed() for r in final],
-           "imperfect": sum(1 for r in final if r.mismatch_rate > 0)}
-    path = os.path.join(ROOT, "tests", "golden", "chain_60k.json")
+           "imperfect": sum(1 for r in final if r.mismatch_rate > 0),
+           "with_indel_notes": sum(1 for r in final if r.variations and any("ins(" in v or "del(" in v for v in r.variations))}
+    path = os.path.join(ROOT, "tests", "golden", name)
     with open(path, "w") as fh:
         json.dump(out, fh)
-    print(path, os.path.getsize(path), out["stage_counts"], out["imperfect"], out["digest"][:16])
+    print(path, os.path.getsize(path), out["stage_counts"], out["imperfect"], out["with_indel_notes"], out["digest"][:16])
 
 
 if __name__ == "__main__":

@@ -1,5 +1,6 @@
 """Host-side glue that was restructured for scale must keep the reference's results."""
 import numpy as np
+import pytest
 
 import bwt_algorithm_b200  # noqa: F401
 from bwt_algorithm_b200 import finders
@@ -319,20 +320,23 @@ def test_canonical_motif_memo_equals_direct_form():
             assert got == ("", "+")
 
 
-def test_postprocessing_chain_equals_reference_golden():
-    """tests/golden/chain_60k.json (oracle/gen_chain_golden.py): the unmodified reference's chain on the 3 166
-    strict-scan calls of a 60 kb planted contig -- stage counts, every field of every surviving record
-    (digest of the dataclass tuples, before and after the final filter) and the BED lines."""
+@pytest.mark.parametrize("fixture", ["chain_60k.json", "chain_indel_30k.json"])
+def test_postprocessing_chain_equals_reference_golden(fixture):
+    """tests/golden/chain_60k.json, chain_indel_30k.json (oracle/gen_chain_golden.py): the unmodified reference's
+    chain on the strict-scan calls of a 60 kb planted contig (3 166 calls) and of a 30 kb contig whose arrays carry
+    insertions and deletions and lie close together (1 749 calls, 28 final calls with ins/del notes) -- stage
+    counts, every field of every surviving record (digest of the dataclass tuples, before and after the final
+    filter) and the BED lines."""
     import dataclasses
     import hashlib
     import json
     import os
 
-    from tests.util import gen_contig
+    from tests import util
 
-    with open(os.path.join(os.path.dirname(__file__), "golden", "chain_60k.json")) as fh:
+    with open(os.path.join(os.path.dirname(__file__), "golden", fixture)) as fh:
         g = json.load(fh)
-    full = gen_contig(g["n"], g["seed"]).tobytes().decode()
+    full = getattr(util, g["generator"])(g["n"], g["seed"]).tobytes().decode()
     seq = full[g["flank"]:len(full) - g["flank"]]
     rows = np.zeros((len(g["rows"]), 8), np.int32)
     rows[:, :4] = np.array(g["rows"], np.int32)

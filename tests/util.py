@@ -20,6 +20,28 @@ def gen_contig(n, seed, sub_rate=0.03):
     return s
 
 
+def gen_contig_indel(n, seed, sub_rate=0.05, indel_rate=0.02, gap=(20, 400)):
+    """Planted arrays of 1-12 bp motifs with substitutions AND single-base insertions / deletions, close together:
+    dense merge chains, re-alignments with ins/del notes, collapsing calls."""
+    rng = np.random.default_rng(seed)
+    A = np.frombuffer(b"ACGT", dtype=np.uint8)
+    s = A[rng.integers(0, 4, n)]
+    pos = 200
+    while pos < n - 400:
+        k = int(rng.integers(1, 13))
+        m = A[rng.integers(0, 4, k)]
+        arr = np.tile(m, int(rng.integers(4, 30)))
+        mut = rng.random(arr.size) < sub_rate
+        arr[mut] = A[rng.integers(0, 4, int(mut.sum()))]
+        for _ in range(int(rng.binomial(arr.size, indel_rate))):
+            at = int(rng.integers(1, max(2, arr.size - 1)))
+            arr = np.insert(arr, at, A[rng.integers(0, 4)]) if rng.random() < 0.5 else np.delete(arr, at)
+        end = min(n, pos + arr.size)
+        s[pos:end] = arr[:end - pos]
+        pos = end + int(rng.integers(gap[0], gap[1]))
+    return s
+
+
 def text_cases():
     """(name, text bytes) -- texts as BWTCore receives them (caller appends '$')."""
     rng = np.random.default_rng(99)
