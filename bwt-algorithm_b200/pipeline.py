@@ -35,7 +35,7 @@ def _elapsed(t0: float) -> str:
 
 def _detect_rows(chrom: str, seq: str, config: dict):
     """One contig at row level: index build + strict adjacency scan (bwt.py:3040-3106).  Returns
-    (rows int32[R, 8] or None when no detector ran, text_arr uint8 incl. '$', max_mismatch)."""
+    (rows int32[R, 8] or None when no detector ran, text_arr uint8 incl. '$' or None when there are no rows)."""
     import numpy as np
 
     from . import lean
