@@ -22,6 +22,10 @@ CASES = [
     ("test_long_motif.fa", [], "test_long_motif"),
     ("test_synthetic.fasta", ["--flank-trim", "0"], "test_synthetic_flank-trim_0"),
 ]
+# a FASTA of our own through the reference CLI (oracle/gen_cli_golden.py: write_syn_mixed): insertions / deletions in
+# closely spaced arrays, lower-case stretches, an N block, IUPAC codes, a contig too short to trim, ragged lines.
+# Host glue only: the detector rows come from the CPU restatement here.
+CPU_CASES = CASES + [("syn_mixed.fa", [], "syn_mixed")]
 FORMATS = ["strfinder", "bed", "vcf", "trf_table", "trf_dat"]
 
 
@@ -30,7 +34,7 @@ def _expected(tag, fmt):
         return f.read()
 
 
-@pytest.mark.parametrize("fa,flags,tag", CASES, ids=[c[2] for c in CASES])
+@pytest.mark.parametrize("fa,flags,tag", CPU_CASES, ids=[c[2] for c in CPU_CASES])
 def test_host_glue_reproduces_reference_outputs(oracle, tmp_path, fa, flags, tag):
     import bwt_algorithm_b200  # noqa: F401
     from bwt_algorithm_b200 import finders
