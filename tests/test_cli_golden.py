@@ -24,8 +24,7 @@ CASES = [
 ]
 # a FASTA of our own through the reference CLI (oracle/gen_cli_golden.py: write_syn_mixed): insertions / deletions in
 # closely spaced arrays, lower-case stretches, an N block, IUPAC codes, a contig too short to trim, ragged lines.
-# Host glue only: the detector rows come from the CPU restatement here.
-CPU_CASES = CASES + [("syn_mixed.fa", [], "syn_mixed")]
+CPU_CASES = CASES + [("syn_mixed.fa", [], "syn_mixed")]       # the host-glue test and the GPU CLI test run all of these
 FORMATS = ["strfinder", "bed", "vcf", "trf_table", "trf_dat"]
 
 
@@ -75,7 +74,7 @@ def test_host_glue_reproduces_reference_outputs(oracle, tmp_path, fa, flags, tag
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("jobs", ["-1", "4"])
-@pytest.mark.parametrize("fa,flags,tag", CASES, ids=[c[2] for c in CASES])
+@pytest.mark.parametrize("fa,flags,tag", CPU_CASES, ids=[c[2] for c in CPU_CASES])
 def test_cli_byte_identical_on_gpu(tmp_path, capsys, fa, flags, tag, jobs):
     import bwt_algorithm_b200  # noqa: F401
     from bwt_algorithm_b200 import bwt
